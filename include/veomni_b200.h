@@ -1,0 +1,101 @@
+/*
+ * veomni_b200 C ABI — the drop-in boundary of the B200-native hot path.
+ *
+ * The reference (ByteDance-Seed/VeOmni) has no native code: its "FFI" for this path is the
+ * set of Python hooks listed in SURVEY.md §8(b) (OpSlot kernels, the Ulysses all-to-all choke
+ * point, the EP dispatch/combine functions, and PyTorch FSDP2's custom AllGather/ReduceScatter
+ * hooks).  Every entry point below is what the Python side of one of those hooks binds through
+ * ctypes (veomni_b200/_lib.py); each cites the reference call site it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all device pointers unless stated otherwise
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *   - return 0 on success, negative VB200_E* on failure; vb200_last_error() has the text
+ *   - no allocation inside compute calls; no hidden global state except the explicit
+ *     vb200_comm handle (peer pointers + signal pads)
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t) unless stated otherwise
+ */
+#ifndef VEOMNI_B200_H_
+#define VEOMNI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_OK 0
+#define VB200_EINVAL (-1)   /* bad argument / unsupported shape */
+#define VB200_ECUDA (-2)    /* CUDA runtime error, see vb200_last_error() */
+#define VB200_ESTATE (-3)   /* comm handle in wrong state */
+#define VB200_ETIMEOUT (-4) /* peer signal wait exceeded its bound */
+
+#define VB200_ABI_VERSION 1
+
+/* ---- runtime ------------------------------------------------------------------------- */
+int vb200_abi_version(void);
+const char* vb200_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+int64_t vb200_launch_count(void);
+void vb200_reset_launch_count(void);
+
+/* ---- RMSNorm --------------------------------------------------------------------------
+ * Replaces OpSlot("rms_norm","standard") (veomni/ops/liger/__init__.py:28-59) i.e.
+ * Qwen3RMSNorm.forward (veomni/models/transformers/qwen3/generated/
+ * patched_modeling_qwen3_gpu.py:88-97):  y = w * bf16(x * rsqrt(mean(x^2) + eps)).
+ * x,y: [rows, cols] bf16 row-major (cols % 8 == 0, cols <= 16384); w: [cols] bf16;
+ * rstd: [rows] fp32 (saved for backward).                                                 */
+int vb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows, int64_t cols,
+                      float eps, void* stream);
+/* dx: [rows, cols] bf16; dw_partial: [vb200_rmsnorm_bwd_partials(rows, cols), cols] fp32
+ * workspace; dw: [cols] fp32 = column sums (deterministic two-pass reduction).            */
+int64_t vb200_rmsnorm_bwd_partials(int64_t rows, int64_t cols);
+int vb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                      float* dw_partial, float* dw, int64_t rows, int64_t cols, void* stream);
+
+/* ---- RoPE -----------------------------------------------------------------------------
+ * Replaces OpSlot("rotary_pos_emb","full") (patched_modeling_qwen3_gpu.py:208-223):
+ *   out = x*cos + rotate_half(x)*sin  for q and k, cos/sin: [tokens, head_dim] bf16.
+ * q,k are addressed as [tokens, heads, head_dim] with explicit element strides so both the
+ * reference's transposed [B,H,S,D] views and packed [S,H,D] buffers work without a copy.
+ * `inverse` != 0 applies the transposed rotation (the backward of the op).
+ * head_dim in {64,128,256}; out may alias in (in-place).                                   */
+int vb200_rope(const void* q_in, void* q_out, const void* k_in, void* k_out, const void* cos,
+               const void* sin, int64_t tokens, int32_t q_heads, int32_t k_heads, int32_t head_dim,
+               int64_t q_stride_tok, int64_t q_stride_head, int64_t k_stride_tok, int64_t k_stride_head,
+               int64_t qo_stride_tok, int64_t qo_stride_head, int64_t ko_stride_tok,
+               int64_t ko_stride_head, int32_t inverse, void* stream);
+
+/* Fused q/k head RMSNorm + RoPE (Qwen3Attention.forward, patched_modeling_qwen3_gpu.py:305-310:
+ * q_norm/k_norm over head_dim followed by apply_rotary_pos_emb) in one pass over q and k.
+ * x: [tokens, heads, head_dim] bf16 contiguous, normalised per (token, head) with weight
+ * wq/wk [head_dim]; rstd_{q,k}: [tokens, heads] fp32 saved for backward.                   */
+int vb200_qknorm_rope_fwd(const void* q_in, const void* k_in, const void* wq, const void* wk,
+                          const void* cos, const void* sin, void* q_out, void* k_out, float* rstd_q,
+                          float* rstd_k, int64_t tokens, int32_t q_heads, int32_t k_heads,
+                          int32_t head_dim, float eps, void* stream);
+int vb200_qknorm_rope_bwd(const void* dq_out, const void* dk_out, const void* q_in, const void* k_in,
+                          const void* wq, const void* wk, const void* cos, const void* sin,
+                          const float* rstd_q, const float* rstd_k, void* dq_in, void* dk_in,
+                          float* dw_partial, float* dwq, float* dwk, int64_t tokens, int32_t q_heads,
+                          int32_t k_heads, int32_t head_dim, void* stream);
+int64_t vb200_qknorm_rope_bwd_partials(int64_t tokens);
+
+/* ---- SwiGLU ---------------------------------------------------------------------------
+ * Replaces the elementwise part of OpSlot("swiglu_mlp","standard")
+ * (veomni/ops/liger/__init__.py:119-142; eager: patched_modeling_qwen3_gpu.py:121-127):
+ *   out = silu(gate) * up.  n elements bf16, n % 8 == 0.
+ * gate/up/out are [rows, cols] with a row stride in elements so a merged [rows, 2*cols]
+ * fc1 output (MoE: EPMergedFc1GroupGemm, veomni/distributed/moe/moe_layer.py:339-346) can be
+ * consumed as two strided views.                                                           */
+int vb200_swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int64_t cols,
+                     int64_t in_stride, int64_t out_stride, void* stream);
+/* dgate = dout * up * dsilu(gate); dup = dout * silu(gate)                                 */
+int vb200_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate, void* dup,
+                     int64_t rows, int64_t cols, int64_t in_stride, int64_t dout_stride,
+                     int64_t dgrad_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VEOMNI_B200_H_ */

@@ -1,0 +1,412 @@
+// RMSNorm forward / backward for sm_100a.
+//
+// Reference semantics: Qwen3RMSNorm.forward
+//   (veomni/models/transformers/qwen3/generated/patched_modeling_qwen3_gpu.py:88-97)
+//     x32 = x.float(); var = mean(x32^2); xhat = x32 * rsqrt(var + eps)
+//     y   = w * xhat.to(bf16)                      (product rounded to bf16)
+//   bound at run time to liger's LigerRMSNormFunction "llama" casting mode
+//   (veomni/ops/liger/__init__.py:28-59), which has the same rounding points.
+//
+// Roofline: pure HBM stream. Forward moves 2*rows*cols*2 B (+cols*2 weight, +rows*4 rstd);
+// backward reads dy,x and writes dx: 3*rows*cols*2 B.
+//
+// Forward, wide rows (cols > 256): persistent warp-per-row kernel. Each warp owns a ring of
+// STAGES row buffers in shared memory filled by 1-D bulk-async copies (TMA engine, SASS UBLKCP)
+// that complete on an mbarrier; the warp reduces sum(x^2) with shuffles, overwrites the row in
+// place with the normalised bf16 values and hands the buffer back to the TMA engine with a
+// bulk shared->global store. No register staging of the row, 3 rows in flight per warp.
+// Forward, narrow rows (cols <= 256, e.g. per-head q/k norm): a group of lanes per row.
+// Backward: threads own columns and walk over rows, so dw accumulates in registers; one
+// __syncthreads per row (double-buffered partials), deterministic two-pass dw reduction.
+#include "common.cuh"
+
+namespace vb {
+
+// ------------------------------------------------------------------------------------------
+// forward, bulk-async staged
+// ------------------------------------------------------------------------------------------
+constexpr int kFwdStages = 3;
+
+__global__ void __launch_bounds__(256, 1)
+rmsnorm_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                        __nv_bfloat16* __restrict__ y, float* __restrict__ rstd, int64_t rows, int cols,
+                        float eps, int warps_per_cta) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row_bytes = (uint32_t)cols * 2u;
+    const int nvec = cols >> 3;
+    // layout: [w row][warps * STAGES rows][mbarriers]
+    uint4* w_s = reinterpret_cast<uint4*>(smem);
+    uint8_t* bufs = smem + row_bytes;
+    uint64_t* bars =
+        reinterpret_cast<uint64_t*>(smem + (size_t)row_bytes * (1 + (size_t)warps_per_cta * kFwdStages));
+
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) w_s[v] = reinterpret_cast<const uint4*>(w)[v];
+    if (lane == 0) {
+        for (int s = 0; s < kFwdStages; ++s) mbar_init(&bars[warp * kFwdStages + s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t gw = (int64_t)blockIdx.x * warps_per_cta + warp;
+    const int64_t GW = (int64_t)gridDim.x * warps_per_cta;
+    uint8_t* my_bufs = bufs + (size_t)warp * kFwdStages * row_bytes;
+    uint64_t* my_bars = bars + warp * kFwdStages;
+
+    if (lane == 0) {
+        for (int s = 0; s < kFwdStages; ++s) {
+            int64_t r = gw + (int64_t)s * GW;
+            if (r < rows) {
+                mbar_expect_tx(&my_bars[s], row_bytes);
+                bulk_g2s(my_bufs + (size_t)s * row_bytes, x + r * cols, row_bytes, &my_bars[s]);
+            }
+        }
+    }
+    const float inv_cols = 1.0f / (float)cols;
+    int it = 0;
+    for (int64_t r = gw; r < rows; r += GW, ++it) {
+        const int s = it % kFwdStages;
+        const uint32_t parity = (uint32_t)(it / kFwdStages) & 1u;
+        uint4* buf = reinterpret_cast<uint4*>(my_bufs + (size_t)s * row_bytes);
+        mbar_wait(&my_bars[s], parity);
+
+        float ss = 0.f;
+        for (int v = lane; v < nvec; v += 32) {
+            float f[8];
+            unpack8(buf[v], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+        }
+        ss = warp_sum(ss);
+        const float rs = rsqrtf(ss * inv_cols + eps);
+        for (int v = lane; v < nvec; v += 32) {
+            float f[8], g[8];
+            unpack8(buf[v], f);
+            unpack8(w_s[v], g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = g[i] * round_bf16(f[i] * rs);
+            buf[v] = pack8(f);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            rstd[r] = rs;
+            bulk_s2g(y + r * cols, buf, row_bytes);
+            bulk_commit();
+            // The buffer written one iteration ago may be refilled once its store has been read.
+            if (it >= 1) {
+                bulk_wait_read<1>();
+                const int ps = (it - 1) % kFwdStages;
+                const int64_t nr = r - GW + (int64_t)kFwdStages * GW;
+                if (nr < rows) {
+                    mbar_expect_tx(&my_bars[ps], row_bytes);
+                    bulk_g2s(my_bufs + (size_t)ps * row_bytes, x + nr * cols, row_bytes, &my_bars[ps]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// forward, narrow rows: TPR lanes per row (TPR power of two <= 32), one 16-byte vector per lane
+// ------------------------------------------------------------------------------------------
+template <int TPR>
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_small_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                         __nv_bfloat16* __restrict__ y, float* __restrict__ rstd, int64_t rows, int cols,
+                         float eps) {
+    const int nvec = cols >> 3;
+    const int sub = threadIdx.x % TPR;
+    const int64_t rows_per_iter = (int64_t)gridDim.x * (blockDim.x / TPR);
+    const bool active = sub < nvec;
+    float wf[8];
+    if (active) unpack8(reinterpret_cast<const uint4*>(w)[sub], wf);
+    const float inv_cols = 1.0f / (float)cols;
+    // Loop bound is uniform per warp when rows_per_iter divides the padded row range; inactive
+    // rows still take part in the shuffles with zeros.
+    const int64_t first = (int64_t)blockIdx.x * (blockDim.x / TPR) + threadIdx.x / TPR;
+    const int64_t padded = (rows + rows_per_iter - 1) / rows_per_iter * rows_per_iter;
+    for (int64_t r = first; r < padded; r += rows_per_iter) {
+        const bool ok = active && r < rows;
+        float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (ok) unpack8(ldg_stream(x + r * cols + sub * 8), f);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
+        ss = group_sum<TPR>(ss);
+        const float rs = rsqrtf(ss * inv_cols + eps);
+        if (ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = wf[i] * round_bf16(f[i] * rs);
+            stg_stream(y + r * cols + sub * 8, pack8(f));
+            if (sub == 0) rstd[r] = rs;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+// Wide rows: the whole CTA works on one row at a time; thread t owns vectors t, t+THREADS, ...
+template <int THREADS, int V>
+__global__ void __launch_bounds__(THREADS)
+rmsnorm_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                        const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
+                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_partial, int64_t rows,
+                        int cols) {
+    constexpr int NW = THREADS / 32;
+    __shared__ float red[2][NW];
+    const int nvec = cols >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float wf[V][8], dwacc[V][8];
+    bool act[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int v = threadIdx.x + k * THREADS;
+        act[k] = v < nvec;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { wf[k][i] = 0.f; dwacc[k][i] = 0.f; }
+        if (act[k]) unpack8(reinterpret_cast<const uint4*>(w)[v], wf[k]);
+    }
+    const float inv_cols = 1.0f / (float)cols;
+    uint4 dyv[V], xv[V];
+    int64_t r = blockIdx.x;
+    if (r < rows) {
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            if (act[k]) {
+                const int64_t off = r * cols + (int64_t)(threadIdx.x + k * THREADS) * 8;
+                dyv[k] = ldg_stream(dy + off);
+                xv[k] = ldg_stream(x + off);
+            }
+    }
+    int it = 0;
+    for (; r < rows; r += gridDim.x, ++it) {
+        const float rs = rstd[r];
+        float g[V][8], xh[V][8];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (act[k]) {
+                float d[8], xx[8];
+                unpack8(dyv[k], d);
+                unpack8(xv[k], xx);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    xh[k][i] = xx[i] * rs;
+                    g[k][i] = d[i] * wf[k][i];
+                    dot = fmaf(g[k][i], xh[k][i], dot);
+                    dwacc[k][i] = fmaf(d[i], round_bf16(xh[k][i]), dwacc[k][i]);
+                }
+            }
+        }
+        // prefetch the next row before the reduction barrier
+        const int64_t nr = r + gridDim.x;
+        if (nr < rows) {
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+                if (act[k]) {
+                    const int64_t off = nr * cols + (int64_t)(threadIdx.x + k * THREADS) * 8;
+                    dyv[k] = ldg_stream(dy + off);
+                    xv[k] = ldg_stream(x + off);
+                }
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) red[it & 1][warp] = dot;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) tot += red[it & 1][i];
+        const float c = tot * inv_cols;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (act[k]) {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = rs * (g[k][i] - xh[k][i] * c);
+                stg_stream(dx + r * cols + (int64_t)(threadIdx.x + k * THREADS) * 8, pack8(o));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        if (act[k]) {
+            float* dst = dw_partial + (int64_t)blockIdx.x * cols + (int64_t)(threadIdx.x + k * THREADS) * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(dwacc[k][0], dwacc[k][1], dwacc[k][2], dwacc[k][3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(dwacc[k][4], dwacc[k][5], dwacc[k][6], dwacc[k][7]);
+        }
+    }
+}
+
+// Narrow rows: TPR lanes per row, CTA of 256 threads handles 256/TPR rows per iteration.
+template <int TPR>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_small_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                         const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
+                         __nv_bfloat16* __restrict__ dx, float* __restrict__ dw_partial, int64_t rows,
+                         int cols) {
+    constexpr int GROUPS = 256 / TPR;
+    __shared__ float acc_s[GROUPS][TPR * 8 + 1];
+    const int nvec = cols >> 3;
+    const int sub = threadIdx.x % TPR, grp = threadIdx.x / TPR;
+    const bool active = sub < nvec;
+    float wf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dwacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) unpack8(reinterpret_cast<const uint4*>(w)[sub], wf);
+    const float inv_cols = 1.0f / (float)cols;
+    const int64_t rows_per_iter = (int64_t)gridDim.x * GROUPS;
+    const int64_t first = (int64_t)blockIdx.x * GROUPS + grp;
+    const int64_t padded = (rows + rows_per_iter - 1) / rows_per_iter * rows_per_iter;
+    for (int64_t r = first; r < padded; r += rows_per_iter) {
+        const bool ok = active && r < rows;
+        float d[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float rs = 0.f;
+        if (ok) {
+            unpack8(ldg_stream(dy + r * cols + sub * 8), d);
+            unpack8(ldg_stream(x + r * cols + sub * 8), xx);
+            rs = rstd[r];
+        }
+        float g[8], xh[8], dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            xh[i] = xx[i] * rs;
+            g[i] = d[i] * wf[i];
+            dot = fmaf(g[i], xh[i], dot);
+            dwacc[i] = fmaf(d[i], round_bf16(xh[i]), dwacc[i]);
+        }
+        dot = group_sum<TPR>(dot);
+        const float c = dot * inv_cols;
+        if (ok) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = rs * (g[i] - xh[i] * c);
+            stg_stream(dx + r * cols + sub * 8, pack8(o));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc_s[grp][sub * 8 + i] = dwacc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < cols; c += 256) {
+        float t = 0.f;
+#pragma unroll 4
+        for (int gI = 0; gI < GROUPS; ++gI) t += acc_s[gI][c];
+        dw_partial[(int64_t)blockIdx.x * cols + c] = t;
+    }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t nparts,
+                              int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float t = 0.f;
+    for (int64_t p = 0; p < nparts; ++p) t += partial[p * cols + c];
+    out[c] = t;
+}
+
+static int bwd_grid(int64_t rows, int cols) {
+    const int nvec = cols >> 3;
+    int64_t g;
+    if (nvec <= 32) {
+        int tpr = 1;
+        while (tpr < nvec) tpr <<= 1;
+        const int groups = 256 / tpr;
+        g = (rows + groups - 1) / groups;
+        if (g > 4 * kNumSMs) g = 4 * kNumSMs;
+    } else {
+        g = rows < 2 * kNumSMs ? rows : 2 * kNumSMs;
+    }
+    return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+template <int TPR>
+static void launch_fwd_small(const void* x, const void* w, void* y, float* rstd, int64_t rows, int cols,
+                             float eps, cudaStream_t st) {
+    const int groups = 256 / TPR;
+    int64_t g = (rows + groups - 1) / groups;
+    if (g > 8 * kNumSMs) g = 8 * kNumSMs;
+    rmsnorm_fwd_small_kernel<TPR><<<(int)g, 256, 0, st>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, rstd, rows, cols, eps);
+}
+
+extern "C" int vb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_t rows,
+                                 int64_t cols, float eps, void* stream) {
+    if (rows < 0 || cols <= 0 || (cols & 7) || cols > 16384)
+        return vb200_set_error(VB200_EINVAL, "rmsnorm_fwd: cols must be a multiple of 8 in (0,16384]");
+    if (rows == 0) return VB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nvec = (int)(cols >> 3);
+    if (nvec <= 32) {
+        if (nvec <= 1) launch_fwd_small<1>(x, w, y, rstd, rows, (int)cols, eps, st);
+        else if (nvec <= 2) launch_fwd_small<2>(x, w, y, rstd, rows, (int)cols, eps, st);
+        else if (nvec <= 4) launch_fwd_small<4>(x, w, y, rstd, rows, (int)cols, eps, st);
+        else if (nvec <= 8) launch_fwd_small<8>(x, w, y, rstd, rows, (int)cols, eps, st);
+        else if (nvec <= 16) launch_fwd_small<16>(x, w, y, rstd, rows, (int)cols, eps, st);
+        else launch_fwd_small<32>(x, w, y, rstd, rows, (int)cols, eps, st);
+    } else {
+        const size_t row_bytes = (size_t)cols * 2;
+        int warps = (int)((200 * 1024 - row_bytes) / (row_bytes * kFwdStages));
+        if (warps > 8) warps = 8;
+        if (warps < 1) return vb200_set_error(VB200_EINVAL, "rmsnorm_fwd: row too wide for smem staging");
+        const size_t smem = row_bytes * (1 + (size_t)warps * kFwdStages) + sizeof(uint64_t) * warps * kFwdStages;
+        static bool attr_set = false;
+        if (!attr_set) {
+            VB_CUDA_TRY(cudaFuncSetAttribute(rmsnorm_fwd_bulk_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        int64_t g = (rows + warps - 1) / warps;
+        if (g > kNumSMs) g = kNumSMs;
+        rmsnorm_fwd_bulk_kernel<<<(int)g, warps * 32, smem, st>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, rstd, rows, (int)cols, eps,
+            warps);
+    }
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int64_t vb200_rmsnorm_bwd_partials(int64_t rows, int64_t cols) {
+    if (cols <= 0 || (cols & 7)) return 0;
+    return bwd_grid(rows, (int)cols);
+}
+
+extern "C" int vb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
+                                 float* dw_partial, float* dw, int64_t rows, int64_t cols, void* stream) {
+    if (rows < 0 || cols <= 0 || (cols & 7) || cols > 16384)
+        return vb200_set_error(VB200_EINVAL, "rmsnorm_bwd: cols must be a multiple of 8 in (0,16384]");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) {
+        VB_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * cols, st));
+        return VB200_OK;
+    }
+    const int nvec = (int)(cols >> 3);
+    const int g = bwd_grid(rows, (int)cols);
+    const __nv_bfloat16 *dy_ = (const __nv_bfloat16*)dy, *x_ = (const __nv_bfloat16*)x,
+                        *w_ = (const __nv_bfloat16*)w;
+    __nv_bfloat16* dx_ = (__nv_bfloat16*)dx;
+#define SMALL(T) rmsnorm_bwd_small_kernel<T><<<g, 256, 0, st>>>(dy_, x_, w_, rstd, dx_, dw_partial, rows, (int)cols)
+#define WIDE(T, V) rmsnorm_bwd_wide_kernel<T, V><<<g, T, 0, st>>>(dy_, x_, w_, rstd, dx_, dw_partial, rows, (int)cols)
+    if (nvec <= 1) SMALL(1);
+    else if (nvec <= 2) SMALL(2);
+    else if (nvec <= 4) SMALL(4);
+    else if (nvec <= 8) SMALL(8);
+    else if (nvec <= 16) SMALL(16);
+    else if (nvec <= 32) SMALL(32);
+    else if (nvec <= 128) WIDE(128, 1);
+    else if (nvec <= 256) WIDE(256, 1);
+    else if (nvec <= 512) WIDE(512, 1);
+    else if (nvec <= 1024) WIDE(512, 2);
+    else WIDE(512, 4);
+#undef SMALL
+#undef WIDE
+    VB_HOST_CHECK_LAUNCH();
+    colsum_kernel<<<(int)((cols + 255) / 256), 256, 0, st>>>(dw_partial, dw, g, (int)cols);
+    vb200_count_launch(2);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
