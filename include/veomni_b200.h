@@ -95,6 +95,25 @@ int vb200_swiglu_bwd(const void* dout, const void* gate, const void* up, void* d
                      int64_t rows, int64_t cols, int64_t in_stride, int64_t dout_stride,
                      int64_t dgrad_stride, void* stream);
 
+/* ---- packed (varlen) causal attention ---------------------------------------------------
+ * Replaces flash_attn_varlen_func as called by flash_attention_forward
+ * (veomni/ops/kernels/attention/__init__.py:304-320 through HF _flash_attention_forward's
+ * padding-free branch): q [total, Hq, D], k/v [total, Hk, D] packed sequences delimited by
+ * cu_seqlens (int32 [num_seqs+1], device), causal inside each sequence, GQA (Hq % Hk == 0),
+ * D in {64,128}.  strides: int64 host array of (token stride, head stride) element pairs for
+ * q,k,v,o (fwd: 8 values) and q,k,v,o,dout,dq,dk,dv (bwd: 16 values); last dim contiguous.
+ * lse: [Hq, total] fp32 = log-sum-exp of scaled scores (natural log), consumed by the backward.
+ * Backward is deterministic (no atomics): delta [Hq,total] fp32 workspace, then dq, dk, dv.  */
+int vb200_attn_varlen_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                          const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,
+                          int32_t q_heads, int32_t k_heads, int32_t head_dim, const int64_t* strides,
+                          float scale, int32_t causal, void* stream);
+int vb200_attn_varlen_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                          const float* lse, float* delta, void* dq, void* dk, void* dv,
+                          const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,
+                          int32_t q_heads, int32_t k_heads, int32_t head_dim, const int64_t* strides,
+                          float scale, int32_t causal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

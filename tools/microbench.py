@@ -1,0 +1,147 @@
+"""Per-kernel timing of the veomni_b200 kernels at the BASELINE sizes (CUDA events, inputs > L2 or rotated).
+
+Usage: python tools/microbench.py [--only rmsnorm,rope,...] [--iters N] — prints one JSON line per kernel:
+algorithmic bytes, microseconds, achieved GB/s and fraction of the measured HBM peak.
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+
+from veomni_b200 import _lib  # noqa: E402
+from veomni_b200 import functional as F  # noqa: E402
+
+BF = torch.bfloat16
+
+
+def peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def time_fn(fn, sets, iters=20, warmup=5):
+    """sets: list of argument tuples rotated so consecutive launches touch different memory (> L2 in total)."""
+    n = len(sets)
+    for i in range(warmup):
+        fn(*sets[i % n])
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(*sets[i % n])
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) * 1e3 / iters  # us
+
+
+def report(name, us, nbytes=None, flops=None):
+    hbm, tf, how = peaks()
+    r = {"kernel": name, "us": round(us, 2)}
+    if nbytes:
+        r["algo_MB"] = round(nbytes / 1e6, 2)
+        r["GBps"] = round(nbytes / us / 1e3, 1)
+        r["frac_hbm"] = round(nbytes / us / 1e3 / hbm, 3)
+    if flops:
+        r["TFLOPs"] = round(flops / us / 1e6, 1)
+        r["frac_tensor"] = round(flops / us / 1e6 / tf, 3)
+    r["peak"] = how
+    print(json.dumps(r), flush=True)
+
+
+def bench_rmsnorm(dev, iters):
+    T, H = 4096, 4096
+    lib = _lib.load()
+    nset = 6  # 6 x (32+32 MB) > 126 MB L2
+    sets = []
+    for _ in range(nset):
+        x = torch.randn(T, H, device=dev, dtype=BF)
+        sets.append((x, torch.empty_like(x), torch.empty(T, device=dev, dtype=torch.float32)))
+    w = torch.ones(H, device=dev, dtype=BF)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def fwd(x, y, r):
+        lib.vb200_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), r.data_ptr(), T, H, 1e-6, st)
+
+    report("rmsnorm_fwd[4096x4096]", time_fn(fwd, sets, iters), nbytes=2 * T * H * 2)
+    nparts = lib.vb200_rmsnorm_bwd_partials(T, H)
+    part = torch.empty(nparts, H, device=dev, dtype=torch.float32)
+    dw = torch.empty(H, device=dev, dtype=torch.float32)
+    bsets = [(x, y, r, torch.empty_like(x)) for (x, y, r) in sets]
+    for x, y, r in sets:
+        fwd(x, y, r)
+
+    def bwd(x, dy, r, dx):
+        lib.vb200_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), r.data_ptr(), dx.data_ptr(), part.data_ptr(),
+                              dw.data_ptr(), T, H, st)
+
+    report("rmsnorm_bwd[4096x4096]", time_fn(bwd, bsets, iters), nbytes=3 * T * H * 2)
+    # per-head norm shape (q heads)
+    R, C = 4096 * 40, 128
+    hs = [(torch.randn(R, C, device=dev, dtype=BF), torch.empty(R, C, device=dev, dtype=BF),
+           torch.empty(R, device=dev, dtype=torch.float32)) for _ in range(4)]
+    wh = torch.ones(C, device=dev, dtype=BF)
+
+    def fwdh(x, y, r):
+        lib.vb200_rmsnorm_fwd(x.data_ptr(), wh.data_ptr(), y.data_ptr(), r.data_ptr(), R, C, 1e-6, st)
+
+    report("rmsnorm_fwd[163840x128]", time_fn(fwdh, hs, iters), nbytes=2 * R * C * 2)
+
+
+def bench_rope(dev, iters):
+    T, Hq, Hk, D = 4096, 32, 8, 128
+    cos = torch.randn(T, D, device=dev, dtype=BF)
+    sin = torch.randn(T, D, device=dev, dtype=BF)
+    sets = [(torch.randn(T, Hq, D, device=dev, dtype=BF), torch.randn(T, Hk, D, device=dev, dtype=BF)) for _ in range(6)]
+    wq = torch.ones(D, device=dev, dtype=BF)
+
+    def rope(q, k):
+        F.apply_rotary_pos_emb(q[None].transpose(1, 2), k[None].transpose(1, 2), cos[None], sin[None])
+
+    report("rope_qk[4096x(32+8)x128]", time_fn(rope, sets, iters), nbytes=2 * T * (Hq + Hk) * D * 2)
+
+    def fused(q, k):
+        F.qknorm_rope(q, k, wq, wq, cos, sin, 1e-6)
+
+    report("qknorm_rope_fwd[4096x(32+8)x128]", time_fn(fused, sets, iters), nbytes=2 * T * (Hq + Hk) * D * 2)
+
+
+def bench_swiglu(dev, iters):
+    T, I = 4096, 12288
+    sets = [(torch.randn(T, I, device=dev, dtype=BF), torch.randn(T, I, device=dev, dtype=BF)) for _ in range(3)]
+    with torch.no_grad():
+        report("swiglu_fwd[4096x12288]", time_fn(lambda g, u: F.silu_mul(g, u), sets, iters), nbytes=3 * T * I * 2)
+
+
+BENCHES = {"rmsnorm": bench_rmsnorm, "rope": bench_rope, "swiglu": bench_swiglu}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=30)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    names = [n for n in a.only.split(",") if n] or list(BENCHES)
+    for n in names:
+        mod = BENCHES.get(n)
+        if mod is None:
+            try:
+                extra = __import__("tools.microbench_extra", fromlist=["BENCHES"]).BENCHES
+                mod = extra[n]
+            except Exception as ex:  # noqa: BLE001
+                print(json.dumps({"kernel": n, "error": str(ex)}))
+                continue
+        mod(dev, a.iters)
+
+
+if __name__ == "__main__":
+    main()

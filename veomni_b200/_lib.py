@@ -46,6 +46,8 @@ SIGNATURES = {
     "vb200_qknorm_rope_bwd_partials": (_I64, [_I64]),
     "vb200_swiglu_fwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
     "vb200_swiglu_bwd": (c_int, [_P] * 5 + [_I64] * 5 + [_P]),
+    "vb200_attn_varlen_fwd": (c_int, [_P] * 6 + [_I32] * 6 + [_P, _F, _I32, _P]),
+    "vb200_attn_varlen_bwd": (c_int, [_P] * 11 + [_I32] * 6 + [_P, _F, _I32, _P]),
 }
 
 
