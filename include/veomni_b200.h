@@ -114,6 +114,53 @@ int vb200_attn_varlen_bwd(const void* q, const void* k, const void* v, const voi
                           int32_t q_heads, int32_t k_heads, int32_t head_dim, const int64_t* strides,
                           float scale, int32_t causal, void* stream);
 
+/* ---- peer-memory runtime (NVLink / NVSwitch) --------------------------------------------
+ * One process per GPU. vb200_symm_alloc returns zeroed device memory that can be exported with
+ * vb200_ipc_get_handle (64-byte opaque handle, exchanged by the host through torch.distributed)
+ * and mapped by peers with vb200_ipc_open_handle.  vb200_comm_create takes, for every rank of the
+ * group, the locally mapped base pointer of that rank's symmetric data region and signal pad
+ * (vb200_comm_signal_bytes() bytes, zero-initialised); entries for `rank` itself are the local
+ * allocations.  world <= 8.  Collectives use `channel` (0..31) as an independent epoch/flag
+ * lane: calls on one channel must be issued in the same order on every rank.  `region_offset`
+ * (256-byte aligned) is where THIS rank's buffer for the call lives inside its own region; it is
+ * published to the peers with the ready flag, so offsets may differ between ranks.            */
+int vb200_symm_alloc(void** ptr, int64_t bytes);
+int vb200_symm_free(void* ptr);
+int vb200_ipc_get_handle(const void* ptr, void* handle64);
+int vb200_ipc_open_handle(const void* handle64, void** ptr);
+int vb200_ipc_close_handle(void* ptr);
+int64_t vb200_comm_signal_bytes(void);
+int vb200_comm_create(void** comm, int32_t rank, int32_t world, void* const* peer_data,
+                      void* const* peer_signal, int64_t data_bytes);
+int vb200_comm_destroy(void* comm);
+int vb200_comm_check(void* comm); /* VB200_ETIMEOUT if a peer wait ever timed out (synchronises) */
+int vb200_comm_barrier(void* comm, int32_t channel, void* stream);
+
+/* FSDP2 unit all-gather, replaces DefaultAllGather.__call__
+ * (torch/distributed/fsdp/_fully_shard/_fsdp_collectives.py:81-95) behind
+ * FSDPModule.set_custom_all_gather: rank p's shard (shard_bytes, any dtype) already sits at
+ * region_offset + p*shard_bytes of its own symmetric region (FSDP's copy-in wrote it there);
+ * on return every rank's region holds all N shards.                                          */
+int vb200_allgather(void* comm, int32_t channel, int64_t region_offset, int64_t shard_bytes,
+                    int32_t num_ctas, void* stream);
+/* FSDP2 unit reduce-scatter, replaces DefaultReduceScatter.__call__ (:116-131) incl. the
+ * AVG / pre-multiplied-SUM scaling (:701-759): every rank holds N chunks of chunk_elems fp32 at
+ * region_offset; out[i] = scale * sum_{p=0..N-1} chunk_rank(p)[i], summed in rank order.      */
+int vb200_reduce_scatter_f32(void* comm, int32_t channel, int64_t region_offset, int64_t chunk_elems,
+                             float scale, float* out, int32_t num_ctas, void* stream);
+/* Strided chunk exchange, replaces dist.all_to_all_single + the reshape/cat copies of
+ * _all_to_all_single (veomni/distributed/sequence_parallel/ulysses.py:86-122).
+ * desc: n_desc x 8 int64 = {src_off, src_rank_stride, src_row_stride, dst pointer,
+ * dst_peer_stride, dst_row_stride, rows, seg_bytes} (bytes; all multiples of 16): for every peer p
+ * and row, copy seg_bytes from p's buffer at src_off + rank*src_rank_stride + row*src_row_stride
+ * to dst + p*dst_peer_stride + row*dst_row_stride.                                            */
+int vb200_all_to_all(void* comm, int32_t channel, int64_t region_offset, int32_t n_desc, const int64_t* desc,
+                     int32_t num_ctas, void* stream);
+/* Variable-size block pull for the EP token exchange (veomni/distributed/moe/comm.py:36-42):
+ * chunks = device array of {int64 src_off, int64 dst_off, int64 bytes, int32 peer, int32 pad}.  */
+int vb200_chunk_pull(void* comm, int32_t channel, int64_t region_offset, const void* chunks, int32_t nchunks,
+                     void* dst, int32_t num_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,203 @@
+"""Multi-GPU parity worker (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_worker.py [--bench]
+
+Checks the NVLink pull collectives against the oracle's definition of each collective (rank-order
+slicing) using NCCL only to move the *expected* data around, then FSDP2 end-to-end with the custom
+comm installed vs PyTorch's default NCCL comm.  Prints ``WORKER OK`` on every rank when all pass.
+"""
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO))
+
+from oracle import comm as o_comm  # noqa: E402  (checker)
+
+
+def gather_all(x):
+    out = [torch.empty_like(x) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, x.contiguous())
+    return out
+
+
+def test_barrier_and_allgather(symm, rank, world, dev):
+    for it in range(3):
+        symm.barrier()
+    for numel in (8, 1000, 4096 * 3 + 2, 1 << 20):
+        for dtype in (torch.bfloat16, torch.float32):
+            out = symm.empty((numel * world,), dtype, arena="fsdp_ag")
+            out.fill_(-1)
+            g = torch.Generator(device="cpu").manual_seed(1000 * rank + numel)
+            shard = torch.randn(numel, generator=g).to(dtype).to(dev)
+            out[rank * numel : (rank + 1) * numel].copy_(shard)
+            symm.all_gather_inplace(out, numel, 0)
+            expect = torch.cat(gather_all(shard))
+            assert torch.equal(out, expect), f"allgather mismatch numel={numel} dtype={dtype}"
+    symm.check()
+
+
+def test_reduce_scatter(symm, rank, world, dev):
+    for chunk in (1, 7, 1024, 4099, 1 << 18):
+        inp = symm.empty((chunk * world,), torch.float32, arena="fsdp_rs")
+        g = torch.Generator(device="cpu").manual_seed(77 * rank + chunk)
+        x = torch.randn(chunk * world, generator=g).to(dev)
+        inp.copy_(x)
+        out = torch.empty(chunk, dtype=torch.float32, device=dev)
+        symm.reduce_scatter_f32(inp, out, 1.0 / world, 1)
+        xs = gather_all(x)
+        # oracle: fixed rank order 0..N-1 in fp32, then the divide (== multiply by 1/world for powers of two)
+        ref = o_comm.fsdp_reduce_scatter([t.cpu() for t in xs], torch.float32, None)[rank] * (1.0 / world)
+        assert torch.equal(out.cpu(), ref), f"reduce_scatter mismatch chunk={chunk}: {(out.cpu() - ref).abs().max()}"
+    symm.check()
+
+
+def test_ulysses(rank, world, dev):
+    from veomni_b200 import ulysses as U
+
+    for (Sl, H, D) in ((6, 4 * world, 8), (128, 8 * world, 128), (33, 2 * world, 64)):
+        g = torch.Generator(device="cpu").manual_seed(5 * rank + Sl)
+        x = torch.randn(Sl, H, D, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+        y = U.gather_seq_scatter_heads(x, seq_dim=0, head_dim=1)
+        xs = [t.cpu() for t in gather_all(x.detach())]
+        ref = o_comm.gather_seq_scatter_heads(xs, seq_dim=0, head_dim=1)[rank]
+        assert torch.equal(y.detach().cpu(), ref), f"ulysses gather_seq_scatter_heads mismatch {Sl, H, D}"
+        z = U.gather_heads_scatter_seq(y, head_dim=1, seq_dim=0)
+        assert torch.equal(z.detach(), x.detach()), "ulysses round trip"
+        # autograd: d/dx of sum(w * y) is the reverse exchange of w
+        w = torch.randn(y.shape, generator=torch.Generator().manual_seed(9 + rank)).to(torch.bfloat16).to(dev)
+        (y * w).sum().backward()
+        ws = [t.cpu() for t in gather_all(w)]
+        gref = o_comm.gather_heads_scatter_seq(ws, head_dim=1, seq_dim=0)[rank]
+        assert torch.equal(x.grad.cpu(), gref), "ulysses backward"
+        # 4-D [1, S, H, D] layout and the fused q/k/v launch
+        q = x.detach()[None]
+        k = x.detach()[None, :, : 2 * world].contiguous()
+        qo, ko, vo = U.gather_seq_scatter_heads_qkv(q, k, k, seq_dim=1, head_dim=2)
+        assert torch.equal(qo[0].cpu(), ref)
+        ks = [t.cpu() for t in gather_all(k[0])]
+        assert torch.equal(ko[0].cpu(), o_comm.gather_seq_scatter_heads(ks, 0, 1)[rank])
+        assert torch.equal(vo, ko)
+
+
+def test_fsdp(rank, world, dev):
+    from torch.distributed.fsdp import MixedPrecisionPolicy, fully_shard
+
+    from veomni_b200.fsdp_comm import install_fsdp_comm
+
+    def build():
+        torch.manual_seed(3)
+        m = torch.nn.Sequential(*[torch.nn.Linear(256, 256, bias=False) for _ in range(4)]).to(dev)
+        mpp = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)
+        for layer in m:
+            fully_shard(layer, mp_policy=mpp)
+        fully_shard(m, mp_policy=mpp)
+        return m
+
+    g = torch.Generator(device="cpu").manual_seed(40 + rank)
+    x = torch.randn(32, 256, generator=g).to(dev)
+    ref_m = build()
+    ref_m(x).float().square().mean().backward()
+    ref = {n: p.grad.to_local().clone() for n, p in ref_m.named_parameters()}
+    m = build()
+    install_fsdp_comm(m)
+    for step in range(2):  # second step exercises buffer reuse
+        for p in m.parameters():
+            p.grad = None
+        out = m(x)
+        out.float().square().mean().backward()
+    torch.cuda.synchronize()
+    for n, p in m.named_parameters():
+        got = p.grad.to_local()
+        # same bf16 GEMMs; only the fp32 summation order of the reduce-scatter differs from NCCL's ring
+        torch.testing.assert_close(got, ref[n], atol=1e-6, rtol=1e-4, msg=lambda s, n=n: f"fsdp grad {n}: {s}")
+
+
+def bench(symm, rank, world, dev):
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        symm.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) / iters], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    res = []
+    U = 192_950_000 // world * world  # Qwen3-8B layer unit
+    out = symm.empty((U,), torch.bfloat16, arena="fsdp_ag")
+    for ctas in (16, 32, 64):
+        ms = timeit(lambda: symm.all_gather_inplace(out, U // world, 0, ctas))
+        nbytes = (world - 1) / world * U * 2
+        res.append({"kernel": f"fsdp_allgather[U=193M bf16,N={world},ctas={ctas}]", "ms": round(ms, 3), "nvlink_in_GBps": round(nbytes / ms / 1e6, 1)})
+    nc = torch.empty(U, dtype=torch.bfloat16, device=dev)
+    ms = timeit(lambda: dist.all_gather_into_tensor(nc, nc[rank * (U // world) : (rank + 1) * (U // world)]))
+    res.append({"kernel": f"(lib) nccl all_gather[U=193M bf16,N={world}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 2 / ms / 1e6, 1)})
+    del out
+    inp = symm.empty((U,), torch.float32, arena="fsdp_rs")
+    o = torch.empty(U // world, dtype=torch.float32, device=dev)
+    for ctas in (16, 32, 64):
+        ms = timeit(lambda: symm.reduce_scatter_f32(inp, o, 1.0 / world, 1, ctas))
+        res.append({"kernel": f"fsdp_reducescatter[U=193M fp32,N={world},ctas={ctas}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 4 / ms / 1e6, 1)})
+    nci = torch.empty(U, dtype=torch.float32, device=dev)
+    ms = timeit(lambda: dist.reduce_scatter_tensor(o, nci, op=dist.ReduceOp.AVG))
+    res.append({"kernel": f"(lib) nccl reduce_scatter[U=193M fp32,N={world}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 4 / ms / 1e6, 1)})
+    del inp
+    from veomni_b200 import ulysses as Uly
+
+    S, Hq, Hk, D = 32768, 32, 8, 128
+    if Hk % world == 0:
+        q = torch.randn(S // world, Hq, D, device=dev, dtype=torch.bfloat16)
+        k = torch.randn(S // world, Hk, D, device=dev, dtype=torch.bfloat16)
+        ms = timeit(lambda: Uly.all_to_all_many([q, k, k], 1, 0))
+        nbytes = (world - 1) / world * (q.numel() + 2 * k.numel()) * 2
+        res.append({"kernel": f"ulysses_a2a_qkv[S=32k,P={world}]", "ms": round(ms, 3), "nvlink_in_GBps": round(nbytes / ms / 1e6, 1)})
+    if rank == 0:
+        for r in res:
+            print(json.dumps(r), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bench", action="store_true")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from veomni_b200.symm import get_symmetric_memory
+
+    symm = get_symmetric_memory(None, (3 << 30) if a.bench else (256 << 20), {"fsdp_ag": 0.3, "fsdp_rs": 0.5, "misc": 0.2})
+    test_barrier_and_allgather(symm, rank, world, dev)
+    test_reduce_scatter(symm, rank, world, dev)
+    test_ulysses(rank, world, dev)
+    try:
+        test_fsdp(rank, world, dev)
+    except Exception:
+        import traceback
+
+        traceback.print_exc()
+        raise
+    symm.check()
+    if a.bench:
+        bench(symm, rank, world, dev)
+    dist.barrier()
+    print(f"WORKER OK rank {rank}/{world}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

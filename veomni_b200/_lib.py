@@ -48,6 +48,20 @@ SIGNATURES = {
     "vb200_swiglu_bwd": (c_int, [_P] * 5 + [_I64] * 5 + [_P]),
     "vb200_attn_varlen_fwd": (c_int, [_P] * 6 + [_I32] * 6 + [_P, _F, _I32, _P]),
     "vb200_attn_varlen_bwd": (c_int, [_P] * 11 + [_I32] * 6 + [_P, _F, _I32, _P]),
+    "vb200_symm_alloc": (c_int, [ctypes.POINTER(_P), _I64]),
+    "vb200_symm_free": (c_int, [_P]),
+    "vb200_ipc_get_handle": (c_int, [_P, _P]),
+    "vb200_ipc_open_handle": (c_int, [_P, ctypes.POINTER(_P)]),
+    "vb200_ipc_close_handle": (c_int, [_P]),
+    "vb200_comm_signal_bytes": (_I64, []),
+    "vb200_comm_create": (c_int, [ctypes.POINTER(_P), _I32, _I32, ctypes.POINTER(_P), ctypes.POINTER(_P), _I64]),
+    "vb200_comm_destroy": (c_int, [_P]),
+    "vb200_comm_check": (c_int, [_P]),
+    "vb200_comm_barrier": (c_int, [_P, _I32, _P]),
+    "vb200_allgather": (c_int, [_P, _I32, _I64, _I64, _I32, _P]),
+    "vb200_reduce_scatter_f32": (c_int, [_P, _I32, _I64, _I64, _F, _P, _I32, _P]),
+    "vb200_all_to_all": (c_int, [_P, _I32, _I64, _I32, _P, _I32, _P]),
+    "vb200_chunk_pull": (c_int, [_P, _I32, _I64, _P, _I32, _P, _I32, _P]),
 }
 
 

@@ -1,0 +1,447 @@
+// NVLink / NVSwitch peer-memory runtime and collectives for sm_100a.
+//
+// One process per GPU. Every rank owns a *symmetric* data region and a small signal pad, both
+// cudaMalloc'd here and exported with CUDA IPC so each peer maps them into its own address space
+// (vb200_symm_* / vb200_ipc_*). A `vb200_comm` handle then holds the N mapped base pointers.
+// Collectives are single kernels that read peers' memory directly with coalesced 16-byte loads
+// over NVLink (pull model) and synchronise with flags in the peers' signal pads
+// (st.release.sys / ld.acquire.sys) instead of NCCL's channel/proxy machinery:
+//
+//   vb200_allgather      FSDP2 unit all-gather   (torch/_fsdp_collectives.py:81-95, DefaultAllGather)
+//   vb200_reduce_scatter FSDP2 unit reduce-scatter (:116-131, DefaultReduceScatter) incl. the divide
+//   vb200_all_to_all     Ulysses seq<->head exchange (veomni/distributed/sequence_parallel/ulysses.py:86-122)
+//                        and any chunked pull (EP dispatch/combine row blocks, moe/comm.py:36-42)
+//   vb200_comm_barrier   flag barrier (tests, allocation-lifetime fences)
+//
+// Protocol of every collective kernel on channel c with epoch e (= previous epoch + 1, kept in
+// local device memory, so no host state is needed):
+//   1. ready:  thread p of CTA 0 stores e into peer p's pad[c][READY][my rank]   (release.sys)
+//   2. every CTA waits until its own pad[c][READY][p] >= e for all p             (acquire.sys)
+//   3. pull:   coalesced 16 B loads from peers' regions, local stores
+//   4. done:   the last CTA to finish stores e into every peer's pad[c][DONE][my rank], waits for
+//              all peers' DONE (so when the kernel retires, peers no longer read our region and
+//              it may be overwritten) and publishes epoch[c] = e.
+// Waits are bounded (~30 s of clock64) and report VB200_ETIMEOUT through the comm's error word
+// instead of hanging the GPU.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace vb {
+
+constexpr int kMaxWorld = 8;
+constexpr int kMaxChannels = 32;
+constexpr int kPadWords = kMaxChannels * 2 * kMaxWorld;  // uint64 flag words per rank (4 KB)
+constexpr long long kSpinLimit = 60000000000LL;          // clock64 ticks (~30 s)
+
+struct CommDev {
+    int rank, world;
+    uint8_t* data[kMaxWorld];   // peers' symmetric data regions, mapped locally
+    uint64_t* sig[kMaxWorld];   // peers' signal pads
+    uint32_t* state;            // local: epoch[kMaxChannels], counter[kMaxChannels], error
+};
+
+struct CommHost {
+    CommDev dev;
+    int64_t data_bytes;
+};
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int pad_idx(int ch, int kind, int src) { return (ch * 2 + kind) * kMaxWorld + src; }
+
+// A flag word is {payload:32 (high), epoch:32 (low)}. READY flags carry, as payload, the byte offset
+// >> 8 of the buffer this rank exposes for the collective inside its own symmetric region, so buffer
+// offsets need not be equal across ranks (each rank runs its own allocator).
+// thread t < world: tell peer t that `kind` of epoch e has happened on this rank
+__device__ __forceinline__ void signal_peers(const CommDev& c, int ch, int kind, uint32_t e, int64_t my_off = 0) {
+    if ((int)threadIdx.x < c.world)
+        st_release_sys(c.sig[threadIdx.x] + pad_idx(ch, kind, c.rank), ((uint64_t)(my_off >> 8) << 32) | e);
+}
+// thread t < world: wait until peer t has signalled `kind` of epoch >= e; publishes the peers' payload
+// offsets in shared memory (`peer_off`, may be null) and ends with a block-wide barrier
+__device__ __forceinline__ void wait_peers(const CommDev& c, int ch, int kind, uint32_t e, int64_t* peer_off = nullptr) {
+    if ((int)threadIdx.x < c.world) {
+        const uint64_t* f = c.sig[c.rank] + pad_idx(ch, kind, threadIdx.x);
+        const long long t0 = clock64();
+        uint64_t v;
+        while ((int32_t)((uint32_t)(v = ld_acquire_sys(f)) - e) < 0) {
+            __nanosleep(40);
+            if (clock64() - t0 > kSpinLimit) {
+                atomicExch(c.state + 2 * kMaxChannels, 1u);
+                break;
+            }
+        }
+        if (peer_off) peer_off[threadIdx.x] = (int64_t)(v >> 32) << 8;
+    }
+    __syncthreads();
+}
+// Called by every CTA after its part of the work. Returns true in the last CTA to arrive.
+__device__ __forceinline__ bool grid_arrive_last(const CommDev& c, int ch) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(c.state + kMaxChannels + ch, 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    return is_last != 0;
+}
+__device__ __forceinline__ void finish_epoch(const CommDev& c, int ch, uint32_t e) {
+    // last CTA only
+    signal_peers(c, ch, 1, e);
+    wait_peers(c, ch, 1, e);
+    if (threadIdx.x == 0) {
+        c.state[kMaxChannels + ch] = 0;  // counter
+        __threadfence();
+        c.state[ch] = e;  // epoch
+    }
+}
+
+// Copy `bytes` from src to dst (same alignment modulo 16) with the whole grid; 2-byte granularity.
+__device__ __forceinline__ void grid_copy(uint8_t* dst, const uint8_t* src, int64_t bytes) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    int64_t head = (16 - ((uintptr_t)src & 15)) & 15;
+    if (head > bytes) head = bytes;
+    if (((uintptr_t)src & 15) != ((uintptr_t)dst & 15)) head = bytes;  // fall back to 2-byte copies
+    for (int64_t i = tid * 2; i < head; i += nthr * 2)
+        *reinterpret_cast<uint16_t*>(dst + i) = *reinterpret_cast<const volatile uint16_t*>(src + i);
+    const int64_t nvec = (bytes - head) >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    int64_t i = tid;
+    for (; i + 3 * nthr < nvec; i += 4 * nthr) {  // 4 independent 16 B loads in flight per thread
+        uint4 a = ldg_v4(s4 + i), b = ldg_v4(s4 + i + nthr), c2 = ldg_v4(s4 + i + 2 * nthr),
+              d = ldg_v4(s4 + i + 3 * nthr);
+        d4[i] = a; d4[i + nthr] = b; d4[i + 2 * nthr] = c2; d4[i + 3 * nthr] = d;
+    }
+    for (; i < nvec; i += nthr) d4[i] = ldg_v4(s4 + i);
+    const int64_t done = head + (nvec << 4);
+    for (int64_t j = done + tid * 2; j < bytes; j += nthr * 2)
+        *reinterpret_cast<uint16_t*>(dst + j) = *reinterpret_cast<const volatile uint16_t*>(src + j);
+}
+
+__global__ void __launch_bounds__(512)
+barrier_kernel(CommDev c, int ch) {
+    const uint32_t e = c.state[ch] + 1;
+    signal_peers(c, ch, 0, e);
+    wait_peers(c, ch, 0, e);
+    finish_epoch(c, ch, e);
+}
+
+// All-gather in place inside the symmetric region: rank p's shard already sits at
+// region_p[off_p + p*shard_bytes] of rank p; every rank fills the other N-1 slots from the owners.
+__global__ void __launch_bounds__(512)
+allgather_kernel(CommDev c, int ch, int64_t off, int64_t shard_bytes) {
+    __shared__ int64_t peer_off[kMaxWorld];
+    const uint32_t e = c.state[ch] + 1;
+    if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
+    wait_peers(c, ch, 0, e, peer_off);
+    for (int q = 1; q < c.world; ++q) {
+        const int p = (c.rank + q) % c.world;  // staggered so sources are hit evenly
+        grid_copy(c.data[c.rank] + off + (int64_t)p * shard_bytes, c.data[p] + peer_off[p] + (int64_t)p * shard_bytes,
+                  shard_bytes);
+    }
+    if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
+}
+
+// Reduce-scatter: every rank holds N chunks of `chunk` fp32 values at region[off]; rank r sums
+// chunk r of all ranks in rank order 0..N-1 (deterministic), scales, writes `out` (any memory).
+__global__ void __launch_bounds__(512)
+reduce_scatter_f32_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float scale, float* __restrict__ out) {
+    __shared__ int64_t peer_off[kMaxWorld];
+    const uint32_t e = c.state[ch] + 1;
+    if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
+    wait_peers(c, ch, 0, e, peer_off);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const float* src[kMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kMaxWorld; ++p) {
+        const int pp = p < c.world ? p : 0;
+        src[p] = reinterpret_cast<const float*>(c.data[pp] + peer_off[pp] + (int64_t)c.rank * chunk * 4);
+    }
+    int64_t head = ((16 - ((uintptr_t)src[0] & 15)) & 15) >> 2;  // floats until 16 B alignment
+    if (head > chunk) head = chunk;
+    for (int64_t i = tid; i < head; i += nthr) {
+        float a = 0.f;
+        for (int p = 0; p < c.world; ++p) a += *reinterpret_cast<const volatile float*>(src[p] + i);
+        out[i] = a * scale;
+    }
+    const int64_t nvec = (chunk - head) >> 2;
+    const bool out_aligned = (((uintptr_t)(out + head)) & 15) == 0;
+    for (int64_t v = tid; v < nvec; v += nthr) {
+        uint4 r[kMaxWorld];
+#pragma unroll
+        for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) r[p] = ldg_v4(reinterpret_cast<const uint4*>(src[p] + head) + v);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) {
+                a.x += __uint_as_float(r[p].x); a.y += __uint_as_float(r[p].y);
+                a.z += __uint_as_float(r[p].z); a.w += __uint_as_float(r[p].w);
+            }
+        a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+        float* o = out + head + v * 4;
+        if (out_aligned) *reinterpret_cast<float4*>(o) = a;
+        else { o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; }
+    }
+    for (int64_t i = head + (nvec << 2) + tid; i < chunk; i += nthr) {
+        float a = 0.f;
+        for (int p = 0; p < c.world; ++p) a += *reinterpret_cast<const volatile float*>(src[p] + i);
+        out[i] = a * scale;
+    }
+    if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
+}
+
+// Chunked pull ("all-to-all"): for each descriptor d and each peer p, copy `rows` segments of
+// seg_bytes from peer p's exposed buffer at  src_off + rank*src_rank_stride + row*src_row_stride
+// to local memory at               dst + p*dst_peer_stride + row*dst_row_stride.
+struct A2ADesc {
+    int64_t src_off, src_rank_stride, src_row_stride;
+    uint8_t* dst;
+    int64_t dst_peer_stride, dst_row_stride;
+    int64_t rows, seg_bytes;
+};
+struct A2AArgs {
+    int n;
+    A2ADesc d[4];
+};
+
+__global__ void __launch_bounds__(512)
+all_to_all_kernel(CommDev c, int ch, int64_t off, A2AArgs args) {
+    __shared__ int64_t peer_off[kMaxWorld];
+    const uint32_t e = c.state[ch] + 1;
+    if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
+    wait_peers(c, ch, 0, e, peer_off);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int di = 0; di < args.n; ++di) {
+        const A2ADesc& d = args.d[di];
+        const uint32_t vec_per_seg = (uint32_t)(d.seg_bytes >> 4);
+        const int64_t per_peer = d.rows * vec_per_seg;
+        const int64_t total = per_peer * c.world;
+        // 4 independent 16 B peer loads in flight per thread (NVLink latency ~2 us)
+        for (int64_t i0 = tid; i0 < total; i0 += 4 * nthr) {
+            uint4 val[4];
+            uint4* dstp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + (int64_t)u * nthr;
+                dstp[u] = nullptr;
+                if (i < total) {
+                    const int q = (int)(i / per_peer);
+                    const int p = (c.rank + q) % c.world;
+                    const uint32_t rem = (uint32_t)(i - (int64_t)q * per_peer);
+                    const uint32_t row = rem / vec_per_seg, v = rem - row * vec_per_seg;
+                    val[u] = ldg_v4(reinterpret_cast<const uint4*>(c.data[p] + peer_off[p] + d.src_off +
+                                                                   (int64_t)c.rank * d.src_rank_stride +
+                                                                   (int64_t)row * d.src_row_stride) + v);
+                    dstp[u] = reinterpret_cast<uint4*>(d.dst + (int64_t)p * d.dst_peer_stride +
+                                                       (int64_t)row * d.dst_row_stride) + v;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (dstp[u]) *dstp[u] = val[u];
+        }
+    }
+    if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
+}
+
+// Variable-size chunk pull (EP dispatch / combine): a device-side list of up to `nchunks` copies
+// {peer, src_off (bytes in the peer's region), dst_off (bytes from dst), bytes}; chunk sizes are
+// multiples of 16 bytes. One CTA-group sweeps each chunk; the list itself lives in device memory so
+// it can be produced by the routing kernel without a host round trip.
+struct ChunkDesc {
+    int64_t src_off, dst_off, bytes;
+    int32_t peer, pad;
+};
+
+__global__ void __launch_bounds__(512)
+chunk_pull_kernel(CommDev c, int ch, int64_t off, const ChunkDesc* __restrict__ chunks, int nchunks,
+                  uint8_t* __restrict__ dst) {
+    __shared__ int64_t peer_off[kMaxWorld];
+    const uint32_t e = c.state[ch] + 1;
+    if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
+    wait_peers(c, ch, 0, e, peer_off);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int k = 0; k < nchunks; ++k) {
+        const ChunkDesc d = chunks[k];
+        const int64_t nvec = d.bytes >> 4;
+        const uint4* s = reinterpret_cast<const uint4*>(c.data[d.peer] + peer_off[d.peer] + d.src_off);
+        uint4* o = reinterpret_cast<uint4*>(dst + d.dst_off);
+        int64_t i = tid;
+        for (; i + 3 * nthr < nvec; i += 4 * nthr) {
+            uint4 a = ldg_v4(s + i), b = ldg_v4(s + i + nthr), c2 = ldg_v4(s + i + 2 * nthr), d3 = ldg_v4(s + i + 3 * nthr);
+            o[i] = a; o[i + nthr] = b; o[i + 2 * nthr] = c2; o[i + 3 * nthr] = d3;
+        }
+        for (; i < nvec; i += nthr) o[i] = ldg_v4(s + i);
+    }
+    if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+// ---- allocation / IPC -------------------------------------------------------------------------
+extern "C" int vb200_symm_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return vb200_set_error(VB200_EINVAL, "symm_alloc: bad arguments");
+    VB_CUDA_TRY(cudaMalloc(ptr, (size_t)bytes));
+    VB_CUDA_TRY(cudaMemset(*ptr, 0, (size_t)bytes));
+    VB_CUDA_TRY(cudaDeviceSynchronize());
+    return VB200_OK;
+}
+extern "C" int vb200_symm_free(void* ptr) {
+    VB_CUDA_TRY(cudaFree(ptr));
+    return VB200_OK;
+}
+extern "C" int vb200_ipc_get_handle(const void* ptr, void* handle64) {
+    cudaIpcMemHandle_t h;
+    VB_CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return VB200_OK;
+}
+extern "C" int vb200_ipc_open_handle(const void* handle64, void** ptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    VB_CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return VB200_OK;
+}
+extern "C" int vb200_ipc_close_handle(void* ptr) {
+    VB_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return VB200_OK;
+}
+
+// ---- comm handle ------------------------------------------------------------------------------
+extern "C" int64_t vb200_comm_signal_bytes(void) { return (int64_t)kPadWords * 8; }
+
+extern "C" int vb200_comm_create(void** comm, int32_t rank, int32_t world, void* const* peer_data,
+                                 void* const* peer_signal, int64_t data_bytes) {
+    if (!comm || world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+        return vb200_set_error(VB200_EINVAL, "comm_create: world must be in [1,8] and 0 <= rank < world");
+    CommHost* h = new CommHost();
+    h->dev.rank = rank;
+    h->dev.world = world;
+    for (int p = 0; p < kMaxWorld; ++p) {
+        h->dev.data[p] = (uint8_t*)(p < world ? peer_data[p] : peer_data[rank]);
+        h->dev.sig[p] = (uint64_t*)(p < world ? peer_signal[p] : peer_signal[rank]);
+    }
+    h->data_bytes = data_bytes;
+    const size_t state_bytes = sizeof(uint32_t) * (2 * kMaxChannels + 4);
+    cudaError_t e = cudaMalloc((void**)&h->dev.state, state_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->dev.state, 0, state_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        delete h;
+        return vb200_set_cuda_error(e);
+    }
+    *comm = h;
+    return VB200_OK;
+}
+extern "C" int vb200_comm_destroy(void* comm) {
+    if (!comm) return VB200_OK;
+    CommHost* h = (CommHost*)comm;
+    cudaFree(h->dev.state);
+    delete h;
+    return VB200_OK;
+}
+// Returns VB200_ETIMEOUT if any kernel on this comm ever timed out waiting for a peer (synchronises).
+extern "C" int vb200_comm_check(void* comm) {
+    CommHost* h = (CommHost*)comm;
+    uint32_t err = 0;
+    VB_CUDA_TRY(cudaMemcpy(&err, h->dev.state + 2 * kMaxChannels, 4, cudaMemcpyDeviceToHost));
+    if (err) return vb200_set_error(VB200_ETIMEOUT, "a peer signal wait timed out");
+    return VB200_OK;
+}
+
+static int check_ch(int ch) {
+    if (ch < 0 || ch >= kMaxChannels) return vb200_set_error(VB200_EINVAL, "channel out of range");
+    return 0;
+}
+static int clamp_ctas(int n) { return n < 1 ? 1 : (n > 2 * kNumSMs ? 2 * kNumSMs : n); }
+
+extern "C" int vb200_comm_barrier(void* comm, int32_t channel, void* stream) {
+    if (check_ch(channel)) return VB200_EINVAL;
+    CommHost* h = (CommHost*)comm;
+    barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->dev, channel);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_allgather(void* comm, int32_t channel, int64_t region_offset, int64_t shard_bytes,
+                               int32_t num_ctas, void* stream) {
+    if (check_ch(channel)) return VB200_EINVAL;
+    CommHost* h = (CommHost*)comm;
+    if (region_offset < 0 || (region_offset & 255) || shard_bytes < 0 || (shard_bytes & 1) ||
+        region_offset + shard_bytes * h->dev.world > h->data_bytes)
+        return vb200_set_error(VB200_EINVAL, "allgather: offset must be 256-byte aligned and inside the region");
+    allgather_kernel<<<clamp_ctas(num_ctas), 512, 0, (cudaStream_t)stream>>>(h->dev, channel, region_offset, shard_bytes);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_reduce_scatter_f32(void* comm, int32_t channel, int64_t region_offset, int64_t chunk_elems,
+                                        float scale, float* out, int32_t num_ctas, void* stream) {
+    if (check_ch(channel)) return VB200_EINVAL;
+    CommHost* h = (CommHost*)comm;
+    if (region_offset < 0 || (region_offset & 255) || chunk_elems < 0 ||
+        region_offset + chunk_elems * 4 * h->dev.world > h->data_bytes)
+        return vb200_set_error(VB200_EINVAL, "reduce_scatter: offset must be 256-byte aligned and inside the region");
+    reduce_scatter_f32_kernel<<<clamp_ctas(num_ctas), 512, 0, (cudaStream_t)stream>>>(h->dev, channel, region_offset,
+                                                                                      chunk_elems, scale, out);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_all_to_all(void* comm, int32_t channel, int64_t region_offset, int32_t n_desc,
+                                const int64_t* desc /* n x 8 */, int32_t num_ctas, void* stream) {
+    if (check_ch(channel)) return VB200_EINVAL;
+    if (n_desc < 1 || n_desc > 4) return vb200_set_error(VB200_EINVAL, "all_to_all: 1..4 descriptors");
+    CommHost* h = (CommHost*)comm;
+    A2AArgs a;
+    a.n = n_desc;
+    for (int i = 0; i < n_desc; ++i) {
+        const int64_t* d = desc + 8 * i;
+        a.d[i].src_off = d[0]; a.d[i].src_rank_stride = d[1]; a.d[i].src_row_stride = d[2];
+        a.d[i].dst = (uint8_t*)(uintptr_t)d[3]; a.d[i].dst_peer_stride = d[4]; a.d[i].dst_row_stride = d[5];
+        a.d[i].rows = d[6]; a.d[i].seg_bytes = d[7];
+        if ((d[0] | d[1] | d[2] | d[3] | d[4] | d[5] | d[7]) & 15)
+            return vb200_set_error(VB200_EINVAL, "all_to_all: offsets, strides and segments must be 16-byte multiples");
+        const int64_t last = region_offset + d[0] + (h->dev.world - 1) * d[1] + (d[6] > 0 ? (d[6] - 1) * d[2] : 0) + d[7];
+        if (d[0] < 0 || region_offset < 0 || (region_offset & 255) || last > h->data_bytes)
+            return vb200_set_error(VB200_EINVAL, "all_to_all: source range outside the symmetric region");
+    }
+    all_to_all_kernel<<<clamp_ctas(num_ctas), 512, 0, (cudaStream_t)stream>>>(h->dev, channel, region_offset, a);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_chunk_pull(void* comm, int32_t channel, int64_t region_offset, const void* chunks,
+                                int32_t nchunks, void* dst, int32_t num_ctas, void* stream) {
+    if (check_ch(channel)) return VB200_EINVAL;
+    CommHost* h = (CommHost*)comm;
+    if (region_offset < 0 || (region_offset & 255) || region_offset > h->data_bytes)
+        return vb200_set_error(VB200_EINVAL, "chunk_pull: offset must be 256-byte aligned and inside the region");
+    chunk_pull_kernel<<<clamp_ctas(num_ctas), 512, 0, (cudaStream_t)stream>>>(
+        h->dev, channel, region_offset, (const ChunkDesc*)chunks, nchunks, (uint8_t*)dst);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}

@@ -1,0 +1,190 @@
+"""Ulysses sequence-parallel all-to-all on the NVLink pull kernel.
+
+Mirrors veomni/distributed/sequence_parallel/ulysses.py: ``all_to_all_tensor`` (:125-135) is the
+single choke point VeOmni's ``_SeqAllToAll`` (:138-160), ``gather_seq_scatter_heads`` (:235-253) and
+``gather_heads_scatter_seq`` (:220-232) go through; :func:`install` swaps it for the kernel below, and
+the functions here can also be called directly (same names, same argument meaning).
+
+The reference implements the exchange as reshape/transpose/contiguous + ``all_to_all_single`` +
+split/cat (:96-121): three extra HBM passes around an NCCL send/recv. Here the local tensor is staged
+once into this rank's symmetric region and ONE kernel per call pulls, from every peer, exactly the
+``[rows, seg]`` blocks this rank needs, writing them at their final position of the output tensor.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+import torch.distributed as dist
+
+from ._lib import VB200Error
+from .symm import SymmetricMemory, get_symmetric_memory
+
+CH_ULYSSES = 2
+
+
+def a2a_plan(shape: tuple[int, ...], scatter_dim: int, gather_dim: int, world: int, itemsize: int):
+    """Host-side geometry of the exchange for a contiguous local tensor of ``shape``.
+
+    Returns (out_shape, desc) with desc = (src_rank_stride, src_row_stride, dst_peer_stride,
+    dst_row_stride, rows, seg_bytes) in bytes, or raises for layouts the kernel does not cover.
+    Supported: the two dims are adjacent (in either order) and everything before them has size 1 —
+    i.e. packed ``[S, H, D]`` (dims 0/1) and ``[1, S, H, D]`` (dims 1/2), the layouts VeOmni's attention
+    wrapper produces (veomni/ops/kernels/attention/__init__.py:257-281,322-330).
+    """
+    nd = len(shape)
+    scatter_dim %= nd
+    gather_dim %= nd
+    lo, hi = min(scatter_dim, gather_dim), max(scatter_dim, gather_dim)
+    if hi != lo + 1:
+        raise VB200Error(f"ulysses a2a: scatter/gather dims must be adjacent, got {scatter_dim}/{gather_dim}")
+    for d in shape[:lo]:
+        if d != 1:
+            raise VB200Error("ulysses a2a: leading dims before the exchanged pair must have size 1")
+    inner = itemsize
+    for d in shape[hi + 1:]:
+        inner *= d
+    A, B = shape[lo], shape[hi]  # local [A, B, inner]
+    out = list(shape)
+    if scatter_dim == hi:
+        # gather dim lo (sequence), scatter dim hi (heads): local [Sl, H, *] -> out [P*Sl, H/P, *]
+        if B % world:
+            raise VB200Error(f"ulysses a2a: scattered dim {B} not divisible by the group size {world}")
+        seg = (B // world) * inner
+        desc = (seg, B * inner, A * seg, seg, A, seg)
+        out[lo], out[hi] = A * world, B // world
+    else:
+        # scatter dim lo (sequence), gather dim hi (heads): local [S, Hl, *] -> out [S/P, P*Hl, *]
+        if A % world:
+            raise VB200Error(f"ulysses a2a: scattered dim {A} not divisible by the group size {world}")
+        seg = B * inner
+        rows = A // world
+        desc = (rows * seg, seg, seg, world * seg, rows, seg)
+        out[lo], out[hi] = rows, B * world
+    if seg % 16:
+        raise VB200Error(f"ulysses a2a: segment of {seg} bytes is not a multiple of 16")
+    return tuple(out), desc
+
+
+class _Stage:
+    """Persistent staging buffers in the symmetric region, one per (slot, size)."""
+
+    def __init__(self, symm: SymmetricMemory):
+        self.symm = symm
+        self.bufs: dict[tuple[int, int], torch.Tensor] = {}
+
+    def get(self, slot: int, nbytes: int) -> torch.Tensor:
+        key = (slot, nbytes)
+        if key not in self.bufs:
+            self.bufs[key] = self.symm.empty((nbytes,), torch.uint8, arena="misc")
+        return self.bufs[key]
+
+
+_stages: dict[int, _Stage] = {}
+
+
+def _stage_for(symm: SymmetricMemory) -> _Stage:
+    if id(symm) not in _stages:
+        _stages[id(symm)] = _Stage(symm)
+    return _stages[id(symm)]
+
+
+def all_to_all_many(xs: list[torch.Tensor], scatter_dim: int, gather_dim: int, group: dist.ProcessGroup | None = None,
+                    symm: SymmetricMemory | None = None, num_ctas: int = 32) -> list[torch.Tensor]:
+    """Exchange up to 4 tensors (e.g. q, k, v) in ONE kernel launch."""
+    if not 1 <= len(xs) <= 4:
+        raise VB200Error("all_to_all_many takes 1..4 tensors")
+    symm = symm if symm is not None else get_symmetric_memory(group)
+    world = symm.world
+    if world == 1:
+        return [x for x in xs]
+    stage = _stage_for(symm)
+    outs, descs, base = [], [], None
+    # one staging block holding all inputs back to back (256-byte aligned pieces)
+    sizes = [(x.numel() * x.element_size() + 255) // 256 * 256 for x in xs]
+    buf = stage.get(len(xs), sum(sizes))
+    off = 0
+    for x, sz in zip(xs, sizes):
+        if not x.is_cuda:
+            raise VB200Error("ulysses a2a runs on CUDA tensors only (no gloo/CPU fallback)")
+        out_shape, d = a2a_plan(tuple(x.shape), scatter_dim, gather_dim, world, x.element_size())
+        n = x.numel() * x.element_size()
+        buf[off : off + n].view(x.dtype).view(x.shape).copy_(x)  # stage (one local pass)
+        out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
+        descs.append((off, d[0], d[1], out.data_ptr(), d[2], d[3], d[4], d[5]))
+        outs.append(out)
+        off += sz
+        base = buf
+    symm.all_to_all(base, descs, CH_ULYSSES, num_ctas)
+    return outs
+
+
+def all_to_all_tensor(x: torch.Tensor, scatter_dim: int, gather_dim: int, group: dist.ProcessGroup | None = None,
+                      async_op: bool = False):
+    """Drop-in for veomni.distributed.sequence_parallel.ulysses.all_to_all_tensor (:125-135)."""
+    out = all_to_all_many([x], scatter_dim, gather_dim, group)[0]
+    if async_op:
+        return lambda: out  # stream-ordered: nothing to wait for on the host
+    return out
+
+
+class _SeqAllToAll(torch.autograd.Function):
+    """Same contract as the reference's _SeqAllToAll (ulysses.py:138-160): backward is the reverse exchange."""
+
+    @staticmethod
+    def forward(ctx: Any, group, local_input: torch.Tensor, scatter_dim: int, gather_dim: int) -> torch.Tensor:
+        ctx.group, ctx.scatter_dim, ctx.gather_dim = group, scatter_dim, gather_dim
+        return all_to_all_tensor(local_input, scatter_dim, gather_dim, group)
+
+    @staticmethod
+    def backward(ctx: Any, grad_output: torch.Tensor):
+        return None, all_to_all_tensor(grad_output.contiguous(), ctx.gather_dim, ctx.scatter_dim, ctx.group), None, None
+
+
+class _SeqAllToAllQKV(torch.autograd.Function):
+    """q, k, v exchanged in one launch (forward) and their grads in one launch (backward)."""
+
+    @staticmethod
+    def forward(ctx: Any, group, scatter_dim: int, gather_dim: int, *xs: torch.Tensor):
+        ctx.group, ctx.scatter_dim, ctx.gather_dim = group, scatter_dim, gather_dim
+        return tuple(all_to_all_many(list(xs), scatter_dim, gather_dim, group))
+
+    @staticmethod
+    def backward(ctx: Any, *grads: torch.Tensor):
+        gs = all_to_all_many([g.contiguous() for g in grads], ctx.gather_dim, ctx.scatter_dim, ctx.group)
+        return (None, None, None, *gs)
+
+
+def gather_seq_scatter_heads(x: torch.Tensor, seq_dim: int, head_dim: int, unpadded_dim_size: int = 0, group=None):
+    """Reference: ulysses.py:235-253."""
+    symm = get_symmetric_memory(group)
+    x = _SeqAllToAll.apply(group, x, head_dim, seq_dim)
+    if unpadded_dim_size and unpadded_dim_size % symm.world != 0:
+        x = x.narrow(seq_dim, 0, unpadded_dim_size)
+    return x
+
+
+def gather_seq_scatter_heads_qkv(q, k, v, seq_dim: int, head_dim: int, group=None):
+    """q/k/v variant: one kernel launch for the three tensors."""
+    return _SeqAllToAllQKV.apply(group, head_dim, seq_dim, q, k, v)
+
+
+def gather_heads_scatter_seq(x: torch.Tensor, head_dim: int, seq_dim: int, group=None):
+    """Reference: ulysses.py:220-232 (zero-pads the sequence dim to a multiple of the group size)."""
+    symm = get_symmetric_memory(group)
+    n = x.size(seq_dim)
+    if n % symm.world:
+        pad = list(x.shape)
+        pad[seq_dim] = symm.world - n % symm.world
+        x = torch.cat([x, x.new_zeros(pad)], dim=seq_dim)
+    return _SeqAllToAll.apply(group, x, seq_dim, head_dim)
+
+
+def install() -> None:
+    """Route VeOmni's Ulysses exchange through this module (no-op if VeOmni is not importable)."""
+    try:
+        from veomni.distributed.sequence_parallel import ulysses as ref
+    except ImportError:
+        return
+    ref.all_to_all_tensor = all_to_all_tensor
