@@ -13,6 +13,11 @@ from . import _lib
 from ._lib import VB200Error, check, stream_ptr
 
 
+# When set to a list, every forward launch appends a (start, end) CUDA-event pair recorded on the
+# launching stream (bench.py uses it for the live per-launch duration of the dominant kernel).
+PROFILE = None
+
+
 def _strides(*tensors):
     vals = []
     for t in tensors:
@@ -45,12 +50,19 @@ class _VarlenAttn(torch.autograd.Function):
         scale = float(scale) if scale is not None else 1.0 / math.sqrt(D)
         lib = _lib.load()
         with torch.cuda.device(q.device):
+            if PROFILE is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             check(
                 lib.vb200_attn_varlen_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
                                           cu.data_ptr(), nseq, int(max_seqlen), T, Hq, Hk, D, _strides(q, k, v, o),
                                           scale, 1 if causal else 0, stream_ptr()),
                 "vb200_attn_varlen_fwd",
             )
+            if PROFILE is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                PROFILE.append((ev0, ev1))
         ctx.save_for_backward(q, k, v, o, lse, cu)
         ctx.meta = (int(max_seqlen), scale, bool(causal))
         return o
