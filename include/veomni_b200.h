@@ -161,6 +161,38 @@ int vb200_all_to_all(void* comm, int32_t channel, int64_t region_offset, int32_t
 int vb200_chunk_pull(void* comm, int32_t channel, int64_t region_offset, const void* chunks, int32_t nchunks,
                      void* dst, int32_t num_ctas, void* stream);
 
+/* ---- MoE routing / permutation -----------------------------------------------------------
+ * Replaces expert_histogram + `argsort(stable).argsort()` + moe_scatter / moe_gather of the fused
+ * MoE path (veomni/ops/kernels/moe/group_gemm.py:277-345; kernels in
+ * veomni/ops/kernels/moe/_kernels/kernel/moe.py:53-159,253-333).
+ * expert_index: [num_slots] = flattened [tokens, topk] expert ids (int64 if index_is_int64 else int32).
+ * splits[e] = tokens routed to e; cumsum = inclusive prefix sum of splits; scatter_index[i] = row of
+ * slot i in the expert-sorted activation (stable: ties keep slot order) — integer-exact.
+ * workspace: vb200_moe_route_workspace(num_slots, num_experts) bytes.                          */
+int64_t vb200_moe_route_workspace(int64_t num_slots, int32_t num_experts);
+int vb200_moe_route(const void* expert_index, int32_t index_is_int64, int64_t num_slots, int32_t num_experts,
+                    int32_t* splits, int32_t* cumsum, int32_t* scatter_index, void* workspace, void* stream);
+/* out[scatter_index[t,k], :] = x[t, :]; optionally w_out[scatter_index[t,k]] = w_in[t,k] (bf16).   */
+int vb200_moe_scatter(const void* x, const int32_t* scatter_index, void* out, const void* w_in, void* w_out,
+                      int64_t tokens, int32_t topk, int64_t hidden, void* stream);
+/* out[t,:] = sum_k x[scatter_index[t,k],:] (fp32 accumulation in k order, one rounding); with
+ * weights != NULL each row is first scaled by weights[t,k] and rounded to bf16 (EP combine,
+ * veomni/distributed/moe/moe_utils.py:44-72).                                                  */
+int vb200_moe_gather(const void* x, const int32_t* scatter_index, const void* weights, void* out, int64_t tokens,
+                     int32_t topk, int64_t hidden, void* stream);
+
+/* ---- ragged MoE GroupGEMM (tcgen05 tensor cores) ------------------------------------------
+ * Replaces group_gemm_same_nk / group_gemm_same_mn
+ * (veomni/ops/kernels/moe/_kernels/kernel/group_gemm.py:157-234, 357-397).  bf16 in, fp32 accumulate,
+ * bf16 out.  cumsum: int32 [num_groups] inclusive row prefix (device).  total_rows = rows of `a`.
+ *   mode 0 (NT, transpose_b=True):  c[rows g] = a[rows g] (x k) * b[g]^T,  b [G, n, k]
+ *   mode 1 (NN, transpose_b=False): c[rows g] = a[rows g] (x k) * b[g],    b [G, k, n]
+ *   mode 2 (TN, same_mn wgrad):     c[g] (m x n) = a[rows g]^T * b[rows g], a [rows, m], b [rows, n];
+ *                                   zero-filled when the group is empty.
+ * m, n, k multiples of 8.  Rows of c past cumsum[G-1] are not written.                          */
+int vb200_group_gemm(int32_t mode, const void* a, const void* b, void* c, const int32_t* cumsum,
+                     int32_t num_groups, int64_t total_rows, int32_t m, int32_t n, int32_t k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,7 +55,10 @@ def test_reduce_scatter(symm, rank, world, dev):
         xs = gather_all(x)
         # oracle: fixed rank order 0..N-1 in fp32, then the divide (== multiply by 1/world for powers of two)
         ref = o_comm.fsdp_reduce_scatter([t.cpu() for t in xs], torch.float32, None)[rank] * (1.0 / world)
+        torch.cuda.synchronize()
         assert torch.equal(out.cpu(), ref), f"reduce_scatter mismatch chunk={chunk}: {(out.cpu() - ref).abs().max()}"
+        if rank == 0:
+            print(f"  reduce_scatter chunk={chunk} ok", flush=True)
     symm.check()
 
 
@@ -180,20 +183,36 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     from veomni_b200.symm import get_symmetric_memory
 
-    symm = get_symmetric_memory(None, (3 << 30) if a.bench else (256 << 20), {"fsdp_ag": 0.3, "fsdp_rs": 0.5, "misc": 0.2})
-    test_barrier_and_allgather(symm, rank, world, dev)
-    test_reduce_scatter(symm, rank, world, dev)
-    test_ulysses(rank, world, dev)
-    try:
-        test_fsdp(rank, world, dev)
-    except Exception:
-        import traceback
+    def stage(name, fn, *fa):
+        try:
+            fn(*fa)
+            torch.cuda.synchronize()
+            symm_ref[0] and symm_ref[0].check()
+            print(f"[rank {rank}] stage ok: {name}", flush=True)
+        except Exception:
+            import traceback
 
-        traceback.print_exc()
-        raise
-    symm.check()
+            print(f"[rank {rank}] stage FAILED: {name}", flush=True)
+            traceback.print_exc()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(3)
+
+    symm_ref = [None]
+
+    def make():
+        symm_ref[0] = get_symmetric_memory(None, (3 << 30) if a.bench else (256 << 20),
+                                           {"fsdp_ag": 0.3, "fsdp_rs": 0.5, "misc": 0.2})
+
+    stage("symmetric memory + IPC mapping", make)
+    symm = symm_ref[0]
+    stage("barrier x3", lambda: [symm.barrier() for _ in range(3)])
+    stage("allgather", test_barrier_and_allgather, symm, rank, world, dev)
+    stage("reduce_scatter", test_reduce_scatter, symm, rank, world, dev)
+    stage("ulysses", test_ulysses, rank, world, dev)
+    stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
     if a.bench:
-        bench(symm, rank, world, dev)
+        stage("bench", bench, symm, rank, world, dev)
     dist.barrier()
     print(f"WORKER OK rank {rank}/{world}", flush=True)
     dist.destroy_process_group()

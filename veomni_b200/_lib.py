@@ -48,6 +48,11 @@ SIGNATURES = {
     "vb200_swiglu_bwd": (c_int, [_P] * 5 + [_I64] * 5 + [_P]),
     "vb200_attn_varlen_fwd": (c_int, [_P] * 6 + [_I32] * 6 + [_P, _F, _I32, _P]),
     "vb200_attn_varlen_bwd": (c_int, [_P] * 11 + [_I32] * 6 + [_P, _F, _I32, _P]),
+    "vb200_moe_route_workspace": (_I64, [_I64, _I32]),
+    "vb200_moe_route": (c_int, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _P]),
+    "vb200_moe_scatter": (c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I64, _P]),
+    "vb200_moe_gather": (c_int, [_P, _P, _P, _P, _I64, _I32, _I64, _P]),
+    "vb200_group_gemm": (c_int, [_I32, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P]),
     "vb200_symm_alloc": (c_int, [ctypes.POINTER(_P), _I64]),
     "vb200_symm_free": (c_int, [_P]),
     "vb200_ipc_get_handle": (c_int, [_P, _P]),

@@ -1,0 +1,351 @@
+// Ragged MoE GroupGEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) for sm_100a.
+//
+// Reference: group_gemm_same_nk / group_gemm_same_mn
+//   (veomni/ops/kernels/moe/_kernels/kernel/group_gemm.py:157-234, 357-397; Triton kernels :54-154, :241-354)
+//   used by the fused MoE autograd functions (veomni/ops/kernels/moe/group_gemm.py:269-444) and the EP
+//   variants (veomni/distributed/moe/moe_layer.py:140-441):
+//     mode NT  (fwd)   C[rows g] = A[rows g] (M_g x K) * B[g]^T,  B: [G, N, K]   (transpose_b=True)
+//     mode NN  (dgrad) C[rows g] = A[rows g] (M_g x K) * B[g],    B: [G, K, N]   (transpose_b=False)
+//     mode TN  (wgrad) C[g] (M x N) = A[rows g]^T (M x K_g) * B[rows g] (K_g x N), zero when K_g == 0
+//   bf16 operands, fp32 accumulation, one rounding of the result to bf16.  Rows past cumsum[G-1] are
+//   never written (the reference leaves them unspecified as well).
+//
+// Design: persistent kernel, one CTA per SM, warp-specialised:
+//   warp 0   TMA producer: 128x64 / 64x64 SWIZZLE_128B boxes into a 6-stage smem ring (mbarrier tx-count)
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma (M=128, N=128, K=16, cta_group::1); operands
+//            are read from smem through UMMA descriptors (K-major or MN-major), accumulators live in TMEM
+//            (2 x 128 columns, double-buffered against the epilogue); tcgen05.commit frees smem stages and
+//            hands the accumulator over
+//   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> bf16 -> guarded global stores
+// The tile list (group, m-tile, n-tile) is derived on the device from the cumsum tensor, so no host
+// synchronisation is needed (the reference launches a max_M-sized grid and early-exits, :97-98).
+// Ragged edges: M tails are handled by row guards at the store; the ragged-K tail of mode TN is zeroed in
+// shared memory (A operand rows past the group's end) before the MMA consumes the stage.
+#include "tma.cuh"
+
+namespace vb {
+
+constexpr int GG_BM = 128, GG_BN = 128, GG_BK = 64, GG_STAGES = 6;
+constexpr int GG_STAGE_BYTES = (GG_BM + GG_BN) * GG_BK * 2;  // 32 KB
+constexpr int GG_MAX_G = 1024;
+constexpr int GG_THREADS = 192;
+
+enum { GG_NT = 0, GG_NN = 1, GG_TN = 2 };
+
+struct GGParams {
+    const int* cumsum;  // [G] inclusive
+    int G;
+    int M, N, K;  // NT/NN: N, K = per-group GEMM dims (M unused); TN: M, N = output dims (K unused)
+    __nv_bfloat16* C;
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1
+    // layout_type[61,64)=2 (SWIZZLE_128B); addresses/offsets in 16-byte units
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ constexpr uint32_t umma_idesc(int a_mn_major, int b_mn_major) {
+    // cute::UMMA::InstrDescriptor: c_format[4,6)=1 (F32) a_format[7,10)=1 (BF16) b_format[10,13)=1
+    // a_major bit 15, b_major bit 16, n_dim[17,23)=N>>3, m_dim[24,29)=M>>4
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(GG_BN >> 3) << 17) | ((uint32_t)(GG_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Tile bookkeeping shared by the three roles.
+struct TileInfo {
+    int g, mt, nt;       // group, m-tile, n-tile
+    int row0;            // NT/NN: first A/C row of the tile; TN: first reduction row of the group
+    int rows_valid;      // NT/NN: valid rows in this m-tile (1..128); TN: K_g
+};
+
+template <int MODE>
+__device__ __forceinline__ bool get_tile(int t, const int* tile_start /*smem [G+1]*/, const GGParams& p, int n_tiles_n,
+                                         int m_tiles_tn, TileInfo& ti) {
+    const int total = tile_start[p.G];
+    if (t >= total) return false;
+    if (MODE == GG_TN) {
+        const int per_g = m_tiles_tn * n_tiles_n;
+        ti.g = t / per_g;
+        const int r = t - ti.g * per_g;
+        ti.mt = r / n_tiles_n;
+        ti.nt = r - ti.mt * n_tiles_n;
+        const int s = ti.g ? p.cumsum[ti.g - 1] : 0;
+        ti.row0 = s;
+        ti.rows_valid = p.cumsum[ti.g] - s;
+        return true;
+    }
+    const int mtg = t / n_tiles_n;  // global m-tile index
+    ti.nt = t - mtg * n_tiles_n;
+    int lo = 0, hi = p.G - 1;       // find g with tile_start[g] <= mtg*n_tiles_n < tile_start[g+1]
+    const int key = mtg * n_tiles_n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tile_start[mid + 1] <= key) lo = mid + 1;
+        else hi = mid;
+    }
+    ti.g = lo;
+    ti.mt = mtg - tile_start[lo] / n_tiles_n;
+    const int s = lo ? p.cumsum[lo - 1] : 0;
+    ti.row0 = s + ti.mt * GG_BM;
+    ti.rows_valid = min(GG_BM, p.cumsum[lo] - ti.row0);
+    return true;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GG_THREADS, 1)
+group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GGParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* stages = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GG_STAGES * GG_STAGE_BYTES);
+    uint64_t* empty = full + GG_STAGES;
+    uint64_t* tfull = empty + GG_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    int* tile_start = reinterpret_cast<int*>(tmem_slot + 2);  // [G+1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int n_tiles_n = (p.N + GG_BN - 1) / GG_BN;
+    const int m_tiles_tn = (p.M + GG_BM - 1) / GG_BM;
+    // every thread helps building the tile prefix (G is small)
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int g = 0; g < p.G; ++g) {
+            tile_start[g] = run;
+            if (MODE == GG_TN) run += m_tiles_tn * n_tiles_n;
+            else {
+                const int rows = p.cumsum[g] - (g ? p.cumsum[g - 1] : 0);
+                run += ((rows + GG_BM - 1) / GG_BM) * n_tiles_n;
+            }
+        }
+        tile_start[p.G] = run;
+        for (int s = 0; s < GG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {  // TMEM: 256 columns = two 128-column fp32 accumulators
+        const uint32_t ncols = 256;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            TileInfo ti;
+            for (int t = blockIdx.x; get_tile<MODE>(t, tile_start, p, n_tiles_n, m_tiles_tn, ti); t += gridDim.x) {
+                const int kblocks = (MODE == GG_TN) ? (ti.rows_valid + GG_BK - 1) / GG_BK : (p.K + GG_BK - 1) / GG_BK;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* sa = stages + s * GG_STAGE_BYTES;
+                    uint8_t* sb = sa + GG_BM * GG_BK * 2;
+                    mbar_expect_tx(&full[s], GG_STAGE_BYTES);
+                    if (MODE == GG_TN) {
+                        const int kr = ti.row0 + kb * GG_BK;
+                        tma_load_2d(sa, &tmA, ti.mt * GG_BM, kr, &full[s]);
+                        tma_load_2d(sa + GG_BK * 128, &tmA, ti.mt * GG_BM + 64, kr, &full[s]);
+                        tma_load_2d(sb, &tmB, ti.nt * GG_BN, kr, &full[s]);
+                        tma_load_2d(sb + GG_BK * 128, &tmB, ti.nt * GG_BN + 64, kr, &full[s]);
+                    } else {
+                        tma_load_2d(sa, &tmA, kb * GG_BK, ti.row0, &full[s]);
+                        if (MODE == GG_NT) {
+                            tma_load_3d(sb, &tmB, kb * GG_BK, ti.nt * GG_BN, ti.g, &full[s]);
+                        } else {
+                            tma_load_3d(sb, &tmB, ti.nt * GG_BN, kb * GG_BK, ti.g, &full[s]);
+                            tma_load_3d(sb + GG_BK * 128, &tmB, ti.nt * GG_BN + 64, kb * GG_BK, ti.g, &full[s]);
+                        }
+                    }
+                    if (++s == GG_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = umma_idesc(MODE == GG_TN, MODE != GG_NT);
+        int s = 0, acc = 0;
+        uint32_t ph = 0, aph = 0;
+        TileInfo ti;
+        for (int t = blockIdx.x; get_tile<MODE>(t, tile_start, p, n_tiles_n, m_tiles_tn, ti); t += gridDim.x) {
+            const int kblocks = (MODE == GG_TN) ? (ti.rows_valid + GG_BK - 1) / GG_BK : (p.K + GG_BK - 1) / GG_BK;
+            mbar_wait(&tempty[acc], aph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * GG_BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                uint8_t* sa = stages + s * GG_STAGE_BYTES;
+                uint8_t* sb = sa + GG_BM * GG_BK * 2;
+                if (MODE == GG_TN) {
+                    const int valid = ti.rows_valid - kb * GG_BK;  // reduction rows of this block inside the group
+                    if (valid < GG_BK) {
+                        // zero A's rows [valid, 64): rows of the next group must not contribute
+                        for (int r = valid + (lane >> 4); r < GG_BK; r += 2) {
+                            const int c = lane & 15;  // 16 x 16 B = two 128-byte box rows
+                            *reinterpret_cast<uint4*>(sa + (c >> 3) * GG_BK * 128 + r * 128 + (c & 7) * 16) = make_uint4(0, 0, 0, 0);
+                        }
+                        fence_async_smem();
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
+#pragma unroll
+                    for (int k = 0; k < GG_BK / 16; ++k) {
+                        uint64_t ad, bd;
+                        if (MODE == GG_TN) ad = umma_desc(a_addr + k * 16 * 128, GG_BK * 128, 1024);  // MN-major
+                        else ad = umma_desc(a_addr + k * 32, 16, 1024);                               // K-major
+                        if (MODE == GG_NT) bd = umma_desc(b_addr + k * 32, 16, 1024);
+                        else bd = umma_desc(b_addr + k * 16 * 128, GG_BK * 128, 1024);
+                        umma_f16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++s == GG_STAGES) { s = 0; ph ^= 1; }
+            }
+            if (kblocks == 0 && lane == 0) mbar_arrive(&tfull[acc]);  // empty group (TN): epilogue writes zeros
+            if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
+    } else {
+        // ===== epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =====
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t aph = 0;
+        TileInfo ti;
+        for (int t = blockIdx.x; get_tile<MODE>(t, tile_start, p, n_tiles_n, m_tiles_tn, ti); t += gridDim.x) {
+            const int kblocks = (MODE == GG_TN) ? (ti.rows_valid + GG_BK - 1) / GG_BK : (p.K + GG_BK - 1) / GG_BK;
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const int r = q * 32 + lane;  // row inside the tile
+            bool row_ok;
+            __nv_bfloat16* crow;
+            if (MODE == GG_TN) {
+                const int m = ti.mt * GG_BM + r;
+                row_ok = m < p.M;
+                crow = p.C + ((int64_t)ti.g * p.M + m) * p.N + ti.nt * GG_BN;
+            } else {
+                row_ok = r < ti.rows_valid;
+                crow = p.C + (int64_t)(ti.row0 + r) * p.N + ti.nt * GG_BN;
+            }
+            const int ncols = min(GG_BN, p.N - ti.nt * GG_BN);
+#pragma unroll 1
+            for (int c = 0; c < GG_BN / 32; ++c) {
+                uint32_t v[32];
+                if (kblocks > 0) {
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GG_BN + c * 32, v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                }
+                if (row_ok) {
+                    if (c * 32 + 32 <= ncols) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 o;
+                            o.x = f2_to_bf2(__uint_as_float(v[i * 8 + 0]), __uint_as_float(v[i * 8 + 1]));
+                            o.y = f2_to_bf2(__uint_as_float(v[i * 8 + 2]), __uint_as_float(v[i * 8 + 3]));
+                            o.z = f2_to_bf2(__uint_as_float(v[i * 8 + 4]), __uint_as_float(v[i * 8 + 5]));
+                            o.w = f2_to_bf2(__uint_as_float(v[i * 8 + 6]), __uint_as_float(v[i * 8 + 7]));
+                            *reinterpret_cast<uint4*>(crow + c * 32 + i * 8) = o;
+                        }
+                    } else {
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < ncols) crow[c * 32 + i] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        const uint32_t ncols = 256;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+static size_t gg_smem_bytes(int G) {
+    return (size_t)GG_STAGES * GG_STAGE_BYTES + (2 * GG_STAGES + 4) * 8 + 16 + (size_t)(G + 1) * 4 + 64;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+// a: NT/NN [sumM, K]; TN [sumK, M].   b: NT [G, N, K]; NN [G, K, N]; TN [sumK, N].   c: NT/NN [sumM, N]; TN [G, M, N].
+extern "C" int vb200_group_gemm(int32_t mode, const void* a, const void* b, void* c, const int32_t* cumsum,
+                                int32_t num_groups, int64_t total_rows, int32_t m, int32_t n, int32_t k, void* stream) {
+    if (mode < 0 || mode > 2) return vb200_set_error(VB200_EINVAL, "group_gemm: mode must be 0 (NT), 1 (NN) or 2 (TN)");
+    if (num_groups < 1 || num_groups > GG_MAX_G) return vb200_set_error(VB200_EINVAL, "group_gemm: 1..1024 groups");
+    if (n <= 0 || (n & 7)) return vb200_set_error(VB200_EINVAL, "group_gemm: N must be a positive multiple of 8");
+    if (mode != GG_TN && (k <= 0 || (k & 7))) return vb200_set_error(VB200_EINVAL, "group_gemm: K must be a positive multiple of 8");
+    if (mode == GG_TN && (m <= 0 || (m & 7))) return vb200_set_error(VB200_EINVAL, "group_gemm: M must be a positive multiple of 8");
+    if (total_rows <= 0 && mode != GG_TN) return VB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tmA, tmB;
+    int rc;
+    GGParams p{};
+    p.cumsum = cumsum; p.G = num_groups; p.M = m; p.N = n; p.K = k; p.C = (__nv_bfloat16*)c;
+    const uint64_t rows = (uint64_t)(total_rows > 0 ? total_rows : 1);
+    const size_t smem = gg_smem_bytes(num_groups);
+    if (mode == GG_NT) {
+        if ((rc = make_tmap_2d(&tmA, a, k, rows, k, GG_BM))) return rc;
+        if ((rc = make_tmap_3d_box(&tmB, b, k, n, num_groups, k, (uint64_t)n * k, 64, GG_BN))) return rc;
+        static bool attr = false;
+        if (!attr) { VB_CUDA_TRY(cudaFuncSetAttribute(group_gemm_kernel<GG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+        group_gemm_kernel<GG_NT><<<kNumSMs, GG_THREADS, smem, st>>>(tmA, tmB, p);
+    } else if (mode == GG_NN) {
+        if ((rc = make_tmap_2d(&tmA, a, k, rows, k, GG_BM))) return rc;
+        if ((rc = make_tmap_3d_box(&tmB, b, n, k, num_groups, n, (uint64_t)n * k, 64, GG_BK))) return rc;
+        static bool attr = false;
+        if (!attr) { VB_CUDA_TRY(cudaFuncSetAttribute(group_gemm_kernel<GG_NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+        group_gemm_kernel<GG_NN><<<kNumSMs, GG_THREADS, smem, st>>>(tmA, tmB, p);
+    } else {
+        if ((rc = make_tmap_2d(&tmA, a, m, rows, m, GG_BK))) return rc;
+        if ((rc = make_tmap_2d(&tmB, b, n, rows, n, GG_BK))) return rc;
+        static bool attr = false;
+        if (!attr) { VB_CUDA_TRY(cudaFuncSetAttribute(group_gemm_kernel<GG_TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+        group_gemm_kernel<GG_TN><<<kNumSMs, GG_THREADS, smem, st>>>(tmA, tmB, p);
+    }
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}

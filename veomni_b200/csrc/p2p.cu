@@ -163,26 +163,32 @@ reduce_scatter_f32_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float s
     wait_peers(c, ch, 0, e, peer_off);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-    const float* src[kMaxWorld];
-#pragma unroll
-    for (int p = 0; p < kMaxWorld; ++p) {
-        const int pp = p < c.world ? p : 0;
-        src[p] = reinterpret_cast<const float*>(c.data[pp] + peer_off[pp] + (int64_t)c.rank * chunk * 4);
-    }
-    int64_t head = ((16 - ((uintptr_t)src[0] & 15)) & 15) >> 2;  // floats until 16 B alignment
+    const int64_t rank_base = (int64_t)c.rank * chunk * 4;
+    // All loops over peers are fully unrolled with a predicate so the peer pointers stay in registers.
+#define VB_SRC(p) (c.data[p] + peer_off[p] + rank_base)
+    int64_t head = ((16 - ((uintptr_t)VB_SRC(0) & 15)) & 15) >> 2;  // floats until 16-byte alignment
     if (head > chunk) head = chunk;
-    for (int64_t i = tid; i < head; i += nthr) {
+    const int64_t nvec = (chunk - head) >> 2;
+    const int64_t tail0 = head + (nvec << 2);
+    // scalar head [0, head) and tail [tail0, chunk)
+    for (int64_t j = tid; j < head + (chunk - tail0); j += nthr) {
+        const int64_t i = j < head ? j : tail0 + (j - head);
         float a = 0.f;
-        for (int p = 0; p < c.world; ++p) a += *reinterpret_cast<const volatile float*>(src[p] + i);
+#pragma unroll
+        for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) {
+                float v;
+                asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(VB_SRC(p) + i * 4) : "memory");
+                a += v;
+            }
         out[i] = a * scale;
     }
-    const int64_t nvec = (chunk - head) >> 2;
     const bool out_aligned = (((uintptr_t)(out + head)) & 15) == 0;
     for (int64_t v = tid; v < nvec; v += nthr) {
         uint4 r[kMaxWorld];
 #pragma unroll
         for (int p = 0; p < kMaxWorld; ++p)
-            if (p < c.world) r[p] = ldg_v4(reinterpret_cast<const uint4*>(src[p] + head) + v);
+            if (p < c.world) r[p] = ldg_v4(VB_SRC(p) + (head << 2) + (v << 4));
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int p = 0; p < kMaxWorld; ++p)
@@ -192,14 +198,16 @@ reduce_scatter_f32_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float s
             }
         a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
         float* o = out + head + v * 4;
-        if (out_aligned) *reinterpret_cast<float4*>(o) = a;
-        else { o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; }
+        if (out_aligned) {
+            asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+        } else {
+            asm volatile("st.global.f32 [%0], %1;" ::"l"(o), "f"(a.x) : "memory");
+            asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 1), "f"(a.y) : "memory");
+            asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 2), "f"(a.z) : "memory");
+            asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 3), "f"(a.w) : "memory");
+        }
     }
-    for (int64_t i = head + (nvec << 2) + tid; i < chunk; i += nthr) {
-        float a = 0.f;
-        for (int p = 0; p < c.world; ++p) a += *reinterpret_cast<const volatile float*>(src[p] + i);
-        out[i] = a * scale;
-    }
+#undef VB_SRC
     if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
 }
 

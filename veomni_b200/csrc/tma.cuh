@@ -41,6 +41,23 @@ inline int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t inner, uint64
     return 0;
 }
 
+// bf16 tensor [dim2][dim1][inner] with a 2-D box {box_inner (<= 64), box_rows} inside one dim2 slice
+// (expert weight matrices [G][rows][inner]).
+inline int make_tmap_3d_box(CUtensorMap* m, const void* base, uint64_t inner, uint64_t dim1, uint64_t dim2,
+                            uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box_inner, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return vb200_set_error(VB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {inner, dim1, dim2};
+    cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+    cuuint32_t box[3] = {box_inner, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vb200_set_error(VB200_ECUDA, "cuTensorMapEncodeTiled failed");
+    return 0;
+}
+
 // 2-D bf16 matrix [rows][cols] (cols contiguous, row stride in elements), box = {64, box_rows}.
 inline int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems,
                         uint32_t box_rows) {
