@@ -172,7 +172,9 @@ int vb200_chunk_pull(void* comm, int32_t channel, int64_t region_offset, const v
 int64_t vb200_moe_route_workspace(int64_t num_slots, int32_t num_experts);
 int vb200_moe_route(const void* expert_index, int32_t index_is_int64, int64_t num_slots, int32_t num_experts,
                     int32_t* splits, int32_t* cumsum, int32_t* scatter_index, void* workspace, void* stream);
-/* out[scatter_index[t,k], :] = x[t, :]; optionally w_out[scatter_index[t,k]] = w_in[t,k] (bf16).   */
+/* out[scatter_index[t,k], :] = x[t, :]; with w_in and w_out: also w_out[scatter_index[t,k]] = w_in[t,k];
+ * with w_in only: the copied row is scaled by w_in[t,k] (bf16 rounding) — backward of the weighted
+ * combine (veomni/distributed/moe/moe_utils.py:44-72).                                           */
 int vb200_moe_scatter(const void* x, const int32_t* scatter_index, void* out, const void* w_in, void* w_out,
                       int64_t tokens, int32_t topk, int64_t hidden, void* stream);
 /* out[t,:] = sum_k x[scatter_index[t,k],:] (fp32 accumulation in k order, one rounding); with

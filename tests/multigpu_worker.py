@@ -123,6 +123,80 @@ def test_fsdp(rank, world, dev):
         torch.testing.assert_close(got, ref[n], atol=1e-6, rtol=1e-4, msg=lambda s, n=n: f"fsdp grad {n}: {s}")
 
 
+def test_ep(rank, world, dev):
+    """EP dispatch/combine + expert MLP vs the oracle (and vs the reference run stored in tests/golden/multirank.pt)."""
+    from oracle import moe as o_moe
+    from veomni_b200 import ep as EP
+
+    ctx = EP.EPContext()
+    BF = torch.bfloat16
+    if world == 2:  # the fixture was produced by the reference on a 2-rank gloo group
+        fx = torch.load(REPO / "tests" / "golden" / "multirank.pt", weights_only=False)["ranks"]
+        me = fx[rank]["ep"]
+        E = 8
+        hs, idx, rw = me["hs"].to(BF).to(dev), me["idx"].to(dev), me["rw"].to(dev)
+        tokens, plan = EP.ep_dispatch(ctx, hs, idx, E)
+        assert plan.input_splits == me["input_splits"] and plan.output_splits == me["output_splits"], "EP split sizes"
+        assert torch.equal(tokens.cpu(), me["tokens"].to(BF)), "EP dispatched tokens differ from the reference"
+        final = EP.ep_combine(tokens * 2.0, rw, plan)
+        torch.testing.assert_close(final.float().cpu(), me["final"], atol=3e-2, rtol=3e-2)
+    # larger random case with real expert MLPs, forward + backward
+    E, K, H, I = 8 * world, 4, 256, 128
+    T = 300 + 17 * rank
+    g = torch.Generator().manual_seed(1000 + rank)
+    hs = (0.5 * torch.randn(T, H, generator=g)).to(BF)
+    logits = torch.randn(T, E, generator=g)
+    if rank == 0:
+        logits[:, 1] = -1e9  # nobody on rank 0 picks expert 1
+    rw, idx = torch.topk(torch.softmax(logits, -1), K, dim=-1)
+    rw = (rw / rw.sum(-1, keepdim=True)).to(BF)
+    gw = torch.Generator().manual_seed(7)  # same weights on every rank
+    w1 = (0.1 * torch.randn(E, 2 * I, H, generator=gw)).to(BF)
+    w2 = (0.1 * torch.randn(E, H, I, generator=gw)).to(BF)
+    dy = (0.1 * torch.randn(T, H, generator=g)).to(BF)
+    el = E // world
+    hs_d = hs.to(dev).requires_grad_(True)
+    rw_d = rw.to(dev).requires_grad_(True)
+    w1_d = w1[rank * el : (rank + 1) * el].to(dev).requires_grad_(True)
+    w2_d = w2[rank * el : (rank + 1) * el].to(dev).requires_grad_(True)
+    out = EP.ep_fused_moe_forward(ctx, E, rw_d, idx.to(dev), hs_d, w1_d, w2_d)
+    out.backward(dy.to(dev))
+    torch.cuda.synchronize()
+
+    def gather_var(x):  # variable T per rank
+        lens = [300 + 17 * r for r in range(world)]
+        res = []
+        for r in range(world):
+            buf = torch.empty((lens[r],) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+            if r == rank:
+                buf.copy_(x)
+            dist.broadcast(buf, src=r)
+            res.append(buf.cpu())
+        return res
+
+    all_hs, all_rw, all_idx, all_dy = gather_var(hs.to(dev)), gather_var(rw.to(dev)), gather_var(idx.to(dev)), gather_var(dy.to(dev))
+    # oracle on fp32 copies of the bf16 inputs, all ranks at once
+    hs_f = [t.float().requires_grad_(True) for t in all_hs]
+    rw_f = [t.float().requires_grad_(True) for t in all_rw]
+    w1_f, w2_f = w1.float().requires_grad_(True), w2.float().requires_grad_(True)
+    outs, disp = o_moe.ep_moe_forward(hs_f, rw_f, all_idx, E, w1_f, w2_f)
+    assert plan_equal(EP, ctx, idx.to(dev), E, H, disp[rank])
+    torch.testing.assert_close(out.float().cpu(), outs[rank].detach(), atol=2e-2, rtol=3e-2)
+    torch.autograd.backward(outs, [d.float() for d in all_dy])
+    for name, got, want in (("d_hidden", hs_d.grad, hs_f[rank].grad), ("d_routing", rw_d.grad, rw_f[rank].grad),
+                            ("d_fc1", w1_d.grad, w1_f.grad[rank * el : (rank + 1) * el]),
+                            ("d_fc2", w2_d.grad, w2_f.grad[rank * el : (rank + 1) * el])):
+        sc = max(1e-6, float(want.abs().max()))
+        torch.testing.assert_close(got.float().cpu() / sc, want / sc, atol=5e-2, rtol=5e-2, msg=lambda m, n=name: f"EP {n}: {m}")
+
+
+def plan_equal(EP, ctx, idx, E, H, ref):
+    plan = EP.make_plan(ctx, idx, E, H)
+    ok = plan.input_splits == ref["input_splits"] and plan.output_splits == ref["output_splits"]
+    ok = ok and torch.equal(plan.cumsum_local.cpu().long(), ref["cumsum"].long())
+    return ok
+
+
 def bench(symm, rank, world, dev):
     def timeit(fn, iters=10):
         for _ in range(3):
@@ -211,6 +285,7 @@ def main():
     stage("reduce_scatter", test_reduce_scatter, symm, rank, world, dev)
     stage("ulysses", test_ulysses, rank, world, dev)
     stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
+    stage("expert parallel dispatch/combine", test_ep, rank, world, dev)
     if a.bench:
         stage("bench", bench, symm, rank, world, dev)
     dist.barrier()

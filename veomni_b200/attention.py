@@ -94,3 +94,51 @@ class _VarlenAttn(torch.autograd.Function):
 def flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen: int, softmax_scale: float | None = None, causal: bool = True):
     """q ``[T,Hq,D]``, k/v ``[T,Hkv,D]`` packed bf16; ``cu_seqlens`` int32 ``[nseq+1]``. Returns ``[T,Hq,D]``."""
     return _VarlenAttn.apply(q, k, v, cu_seqlens, max_seqlen, softmax_scale, causal)
+
+
+def flash_attention_forward(module, query, key, value, attention_mask, dropout: float = 0.0, scaling: float | None = None,
+                            sliding_window=None, softcap=None, skip_ulysses: bool = False, **kwargs):
+    """Drop-in for VeOmni's ``flash_attention_forward`` (veomni/ops/kernels/attention/__init__.py:151-332), the
+    function registered in HF ``ALL_ATTENTION_FUNCTIONS`` for the ``veomni_flash_attention_*_with_sp`` names.
+
+    query ``[B,Hq,S,D]``, key/value ``[B,Hkv,S,D]`` (HF layout) -> ``(attn_output [B,S,Hq,D], None)``.
+    Packed ("padding-free") batches only — VeOmni's collator always supplies ``cu_seq_lens_q/k`` and
+    ``max_length_q/k`` (veomni/data/data_collator.py:44-73) — with the Ulysses gather/scatter around the
+    kernel exactly where the reference has it (:232-281, :322-330).
+    """
+    if sliding_window is not None or softcap is not None or dropout:
+        raise VB200Error("veomni_b200 attention: sliding_window / softcap / dropout are not supported")
+    cu = kwargs.get("cu_seq_lens_q")
+    if cu is None or query.shape[0] != 1:
+        raise VB200Error("veomni_b200 attention needs a packed batch (B == 1) with cu_seq_lens_q/max_length_q kwargs")
+    max_len = int(kwargs.get("max_length_q") or 0)
+    is_causal = kwargs.get("is_causal", getattr(module, "is_causal", True))
+    q = query.transpose(1, 2).squeeze(0)  # [S, Hq, D]
+    k = key.transpose(1, 2).squeeze(0)
+    v = value.transpose(1, 2).squeeze(0)
+    group = None
+    if not skip_ulysses:
+        try:
+            from veomni.distributed.parallel_state import get_parallel_state
+
+            ps = get_parallel_state()
+            if ps.ulysses_enabled:
+                group = ps.ulysses_group
+        except ImportError:
+            group = getattr(module, "ulysses_group", None)
+    if group is not None:
+        from . import ulysses as U
+
+        P = torch.distributed.get_world_size(group)
+        if q.shape[1] % P:
+            raise VB200Error(f"num_query_heads ({q.shape[1]}) must be divisible by ulysses_size ({P})")
+        if P > k.shape[1]:  # KV head replication (:245-255)
+            k = torch.repeat_interleave(k, P // k.shape[1], dim=1)
+            v = torch.repeat_interleave(v, P // v.shape[1], dim=1)
+        q, k, v = U.gather_seq_scatter_heads_qkv(q.contiguous(), k.contiguous(), v.contiguous(), seq_dim=0, head_dim=1, group=group)
+    if max_len <= 0:
+        max_len = int((cu[1:] - cu[:-1]).max())
+    o = flash_attn_varlen(q, k, v, cu, max_len, scaling, bool(is_causal))
+    if group is not None:
+        o = U.gather_heads_scatter_seq(o, head_dim=1, seq_dim=0, group=group)
+    return o.unsqueeze(0), None

@@ -91,20 +91,32 @@ route_rank_kernel(const IdxT* __restrict__ idx, int64_t n, int E, const int* __r
     }
 }
 
-// out[index[t,k]] = x[t]  (+ optional per-slot weight scatter)
+// out[index[t,k]] = x[t]; with w_in: either also scatter the per-slot weight (w_out != null) or, when
+// w_out == null, scale the copied row by w_in[t,k] (rounded to bf16) — the backward of the weighted combine.
 __global__ void __launch_bounds__(256)
 moe_scatter_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ index, __nv_bfloat16* __restrict__ out,
                    const __nv_bfloat16* __restrict__ w_in, __nv_bfloat16* __restrict__ w_out, int64_t T, int K,
                    int vec_per_row) {
+    const bool scale = (w_in != nullptr) && (w_out == nullptr);
     for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
         for (int v = threadIdx.x; v < vec_per_row; v += blockDim.x) {
             const uint4 val = ldg_stream(x + t * vec_per_row * 8 + v * 8);
+            float f[8];
+            if (scale) unpack8(val, f);
             for (int k = 0; k < K; ++k) {
                 const int64_t r = index[t * K + k];
-                stg_stream(out + r * vec_per_row * 8 + v * 8, val);
+                if (scale) {
+                    const float wk = __bfloat162float(w_in[t * K + k]);
+                    float g[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) g[i] = f[i] * wk;
+                    stg_stream(out + r * vec_per_row * 8 + v * 8, pack8(g));
+                } else {
+                    stg_stream(out + r * vec_per_row * 8 + v * 8, val);
+                }
             }
         }
-        if (w_in != nullptr && threadIdx.x < K) w_out[index[t * K + threadIdx.x]] = w_in[t * K + threadIdx.x];
+        if (w_out != nullptr && w_in != nullptr && threadIdx.x < K) w_out[index[t * K + threadIdx.x]] = w_in[t * K + threadIdx.x];
     }
 }
 

@@ -118,10 +118,12 @@ __device__ __forceinline__ void grid_copy(uint8_t* dst, const uint8_t* src, int6
     const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
     uint4* d4 = reinterpret_cast<uint4*>(dst + head);
     int64_t i = tid;
-    for (; i + 3 * nthr < nvec; i += 4 * nthr) {  // 4 independent 16 B loads in flight per thread
-        uint4 a = ldg_v4(s4 + i), b = ldg_v4(s4 + i + nthr), c2 = ldg_v4(s4 + i + 2 * nthr),
-              d = ldg_v4(s4 + i + 3 * nthr);
-        d4[i] = a; d4[i + nthr] = b; d4[i + 2 * nthr] = c2; d4[i + 3 * nthr] = d;
+    for (; i + 7 * nthr < nvec; i += 8 * nthr) {  // 8 independent 16 B peer loads in flight per thread
+        uint4 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = ldg_v4(s4 + i + u * nthr);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d4[i + u * nthr] = r[u];
     }
     for (; i < nvec; i += nthr) d4[i] = ldg_v4(s4 + i);
     const int64_t done = head + (nvec << 4);
@@ -153,14 +155,18 @@ allgather_kernel(CommDev c, int ch, int64_t off, int64_t shard_bytes) {
     if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
 }
 
-// Reduce-scatter: every rank holds N chunks of `chunk` fp32 values at region[off]; rank r sums
-// chunk r of all ranks in rank order 0..N-1 (deterministic), scales, writes `out` (any memory).
+// Reduce-scatter: every rank holds N chunks of `chunk` fp32 values at its buffer; rank r sums chunk r of
+// all ranks in rank order 0..N-1 (deterministic), scales, writes `out` (any memory).
+// W = compile-time world size (0 = generic up to 8), UN = vectors per thread per iteration: UN*W = 8
+// independent 16-byte peer loads are in flight per thread (NVLink latency ~2 us).
+template <int W, int UN>
 __global__ void __launch_bounds__(512)
 reduce_scatter_f32_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float scale, float* __restrict__ out) {
     __shared__ int64_t peer_off[kMaxWorld];
     const uint32_t e = c.state[ch] + 1;
     if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
     wait_peers(c, ch, 0, e, peer_off);
+    constexpr int NP = W ? W : kMaxWorld;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     const int64_t rank_base = (int64_t)c.rank * chunk * 4;
@@ -175,7 +181,7 @@ reduce_scatter_f32_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float s
         const int64_t i = j < head ? j : tail0 + (j - head);
         float a = 0.f;
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
+        for (int p = 0; p < NP; ++p)
             if (p < c.world) {
                 float v;
                 asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(VB_SRC(p) + i * 4) : "memory");
@@ -184,27 +190,37 @@ reduce_scatter_f32_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float s
         out[i] = a * scale;
     }
     const bool out_aligned = (((uintptr_t)(out + head)) & 15) == 0;
-    for (int64_t v = tid; v < nvec; v += nthr) {
-        uint4 r[kMaxWorld];
+    for (int64_t v0 = tid; v0 < nvec; v0 += nthr * UN) {
+        uint4 r[UN][NP];
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-            if (p < c.world) r[p] = ldg_v4(VB_SRC(p) + (head << 2) + (v << 4));
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < UN; ++u) {
+            const int64_t v = v0 + (int64_t)u * nthr;
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-            if (p < c.world) {
-                a.x += __uint_as_float(r[p].x); a.y += __uint_as_float(r[p].y);
-                a.z += __uint_as_float(r[p].z); a.w += __uint_as_float(r[p].w);
+            for (int p = 0; p < NP; ++p)
+                if (p < c.world && v < nvec) r[u][p] = ldg_v4(VB_SRC(p) + (head << 2) + (v << 4));
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int64_t v = v0 + (int64_t)u * nthr;
+            if (v < nvec) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                    if (p < c.world) {
+                        a.x += __uint_as_float(r[u][p].x); a.y += __uint_as_float(r[u][p].y);
+                        a.z += __uint_as_float(r[u][p].z); a.w += __uint_as_float(r[u][p].w);
+                    }
+                a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+                float* o = out + head + v * 4;
+                if (out_aligned) {
+                    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+                } else {
+                    asm volatile("st.global.f32 [%0], %1;" ::"l"(o), "f"(a.x) : "memory");
+                    asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 1), "f"(a.y) : "memory");
+                    asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 2), "f"(a.z) : "memory");
+                    asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 3), "f"(a.w) : "memory");
+                }
             }
-        a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
-        float* o = out + head + v * 4;
-        if (out_aligned) {
-            asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-        } else {
-            asm volatile("st.global.f32 [%0], %1;" ::"l"(o), "f"(a.x) : "memory");
-            asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 1), "f"(a.y) : "memory");
-            asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 2), "f"(a.z) : "memory");
-            asm volatile("st.global.f32 [%0], %1;" ::"l"(o + 3), "f"(a.w) : "memory");
         }
     }
 #undef VB_SRC
@@ -231,36 +247,40 @@ all_to_all_kernel(CommDev c, int ch, int64_t off, A2AArgs args) {
     const uint32_t e = c.state[ch] + 1;
     if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
     wait_peers(c, ch, 0, e, peer_off);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t GW = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int R = 8;  // row segments in flight per warp (one 16 B load per lane each)
     for (int di = 0; di < args.n; ++di) {
         const A2ADesc& d = args.d[di];
-        const uint32_t vec_per_seg = (uint32_t)(d.seg_bytes >> 4);
-        const int64_t per_peer = d.rows * vec_per_seg;
-        const int64_t total = per_peer * c.world;
-        // 4 independent 16 B peer loads in flight per thread (NVLink latency ~2 us)
-        for (int64_t i0 = tid; i0 < total; i0 += 4 * nthr) {
-            uint4 val[4];
-            uint4* dstp[4];
+        const int vec_per_seg = (int)(d.seg_bytes >> 4);
+        const int64_t items = d.rows * c.world;  // (peer slot q, row)
+        for (int64_t it0 = gw * R; it0 < items; it0 += GW * R) {
+            const uint4* srcp[R];
+            uint4* dstp[R];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t i = i0 + (int64_t)u * nthr;
+            for (int u = 0; u < R; ++u) {
+                const int64_t it = it0 + u;
+                srcp[u] = nullptr;
                 dstp[u] = nullptr;
-                if (i < total) {
-                    const int q = (int)(i / per_peer);
-                    const int p = (c.rank + q) % c.world;
-                    const uint32_t rem = (uint32_t)(i - (int64_t)q * per_peer);
-                    const uint32_t row = rem / vec_per_seg, v = rem - row * vec_per_seg;
-                    val[u] = ldg_v4(reinterpret_cast<const uint4*>(c.data[p] + peer_off[p] + d.src_off +
-                                                                   (int64_t)c.rank * d.src_rank_stride +
-                                                                   (int64_t)row * d.src_row_stride) + v);
-                    dstp[u] = reinterpret_cast<uint4*>(d.dst + (int64_t)p * d.dst_peer_stride +
-                                                       (int64_t)row * d.dst_row_stride) + v;
+                if (it < items) {
+                    const int q = (int)(it / d.rows);
+                    const int64_t row = it - (int64_t)q * d.rows;
+                    const int p = (c.rank + q) % c.world;  // staggered over sources
+                    srcp[u] = reinterpret_cast<const uint4*>(c.data[p] + peer_off[p] + d.src_off +
+                                                             (int64_t)c.rank * d.src_rank_stride + row * d.src_row_stride);
+                    dstp[u] = reinterpret_cast<uint4*>(d.dst + (int64_t)p * d.dst_peer_stride + row * d.dst_row_stride);
                 }
             }
+            for (int v = lane; v < vec_per_seg; v += 32) {
+                uint4 val[R];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (dstp[u]) *dstp[u] = val[u];
+                for (int u = 0; u < R; ++u)
+                    if (srcp[u]) val[u] = ldg_v4(srcp[u] + v);
+#pragma unroll
+                for (int u = 0; u < R; ++u)
+                    if (dstp[u]) dstp[u][v] = val[u];
+            }
         }
     }
     if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
@@ -290,9 +310,12 @@ chunk_pull_kernel(CommDev c, int ch, int64_t off, const ChunkDesc* __restrict__ 
         const uint4* s = reinterpret_cast<const uint4*>(c.data[d.peer] + peer_off[d.peer] + d.src_off);
         uint4* o = reinterpret_cast<uint4*>(dst + d.dst_off);
         int64_t i = tid;
-        for (; i + 3 * nthr < nvec; i += 4 * nthr) {
-            uint4 a = ldg_v4(s + i), b = ldg_v4(s + i + nthr), c2 = ldg_v4(s + i + 2 * nthr), d3 = ldg_v4(s + i + 3 * nthr);
-            o[i] = a; o[i + nthr] = b; o[i + 2 * nthr] = c2; o[i + 3 * nthr] = d3;
+        for (; i + 7 * nthr < nvec; i += 8 * nthr) {
+            uint4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] = ldg_v4(s + i + u * nthr);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[i + u * nthr] = r[u];
         }
         for (; i < nvec; i += nthr) o[i] = ldg_v4(s + i);
     }
@@ -410,8 +433,14 @@ extern "C" int vb200_reduce_scatter_f32(void* comm, int32_t channel, int64_t reg
     if (region_offset < 0 || (region_offset & 255) || chunk_elems < 0 ||
         region_offset + chunk_elems * 4 * h->dev.world > h->data_bytes)
         return vb200_set_error(VB200_EINVAL, "reduce_scatter: offset must be 256-byte aligned and inside the region");
-    reduce_scatter_f32_kernel<<<clamp_ctas(num_ctas), 512, 0, (cudaStream_t)stream>>>(h->dev, channel, region_offset,
-                                                                                      chunk_elems, scale, out);
+    const int g = clamp_ctas(num_ctas);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->dev.world) {
+        case 1: reduce_scatter_f32_kernel<1, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        case 2: reduce_scatter_f32_kernel<2, 4><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        case 4: reduce_scatter_f32_kernel<4, 2><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        default: reduce_scatter_f32_kernel<0, 1><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+    }
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;

@@ -1,0 +1,269 @@
+"""Expert-parallel MoE dispatch / combine over NVLink peer memory.
+
+Mirrors the EP branch of ``group_gemm_fused_moe_forward`` (veomni/ops/kernels/moe/group_gemm.py:468-524):
+``preprocess`` -> ``token_pre_all2all`` -> ``EPMergedFc1GroupGemm`` -> ``tokens_post_all2all``
+(veomni/distributed/moe/moe_layer.py:30-137, 307-441; moe_utils.py:19-99; comm.py:20-54), with the same
+results and the same semantics (routing weight applied AFTER the return exchange, fp32 accumulation over
+the top-k, expert-major / source-rank-minor order of the received tokens).
+
+What differs is the machinery.  The reference permutes with masked_select/index_select, calls NCCL
+``all_to_all_single`` with split sizes obtained through two device->host syncs, and regroups with
+split+cat.  Here:
+  1. the routing kernel (moe_route.cu) produces the expert-sorted order in one pass and the row scatter
+     writes the permuted tokens straight into this rank's symmetric send buffer;
+  2. the per-expert counts of all ranks are all-gathered through the symmetric region (512 B / rank);
+     ONE device->host read of that [EP, E] matrix sizes the receive tensor (the reference needs two);
+  3. one pull kernel (vb200_chunk_pull) copies, from every source rank, each (source, local expert)
+     block to its final position — permute + all-to-all + sort_chunks fused, no intermediate copies;
+  4. the return path pulls every (expert, source) block back from the owner's symmetric output buffer and
+     the weighted top-k reduction (moe_gather with weights) replaces unpermute's scatter_add.
+Backward uses the same two block lists in the opposite roles.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import functional as F
+from ._lib import VB200Error, check, stream_ptr
+from .moe import _gather_raw, group_gemm_same_mn, group_gemm_same_nk, moe_route
+from .symm import SymmetricMemory, get_symmetric_memory
+
+CH_EP_COUNTS = 3
+CH_EP_DISPATCH = 4
+CH_EP_COMBINE = 5
+BF = torch.bfloat16
+
+
+class EPContext:
+    """Expert-parallel group state: symmetric region + persistent staging buffers."""
+
+    def __init__(self, group: dist.ProcessGroup | None = None, symm: SymmetricMemory | None = None, num_ctas: int = 32):
+        self.group = group if group is not None else dist.group.WORLD
+        self.symm = symm if symm is not None else get_symmetric_memory(self.group)
+        self.ep_size = self.symm.world
+        self.rank = self.symm.rank
+        self.num_ctas = num_ctas
+        self._bufs: dict[tuple[str, int], torch.Tensor] = {}
+
+    def staging(self, tag: str, nbytes: int) -> torch.Tensor:
+        """Persistent symmetric buffer per (tag, size): reuse is ordered by the collectives' own barriers."""
+        nbytes = (nbytes + 255) // 256 * 256
+        key = (tag, nbytes)
+        if key not in self._bufs:
+            self._bufs[key] = self.symm.empty((nbytes,), torch.uint8, arena="misc")
+        return self._bufs[key]
+
+
+@dataclass
+class EPPlan:
+    """Everything derived from the routing of one MoE layer call (no autograd state)."""
+
+    ctx: EPContext
+    T: int
+    K: int
+    H: int
+    sidx: torch.Tensor                # [T, K] int32: row of slot (t,k) in the local expert-major order
+    counts: torch.Tensor              # [EP, E] int64 on host: tokens rank s sends to expert e
+    input_splits: list                # [EP] rows this rank sends to each rank      (moe_layer.py:41)
+    output_splits: list               # [EP] rows this rank receives from each rank (moe_layer.py:58)
+    total_recv: int
+    cumsum_local: torch.Tensor        # [E/EP] int32 device: inclusive prefix of rows per local expert
+    fwd_chunks: torch.Tensor          # device ChunkDesc list: owner pulls (source, local expert) blocks
+    n_fwd: int
+    bwd_chunks: torch.Tensor          # device ChunkDesc list: source pulls (expert, me) blocks back
+    n_bwd: int
+
+
+def _chunk_tensor(chunks: list[tuple[int, int, int, int]], dev) -> torch.Tensor:
+    """[(peer, src_off, dst_off, bytes)] -> device int64 [n, 4] laid out as the C struct ChunkDesc."""
+    if not chunks:
+        return torch.zeros(1, 4, dtype=torch.int64, device=dev)
+    rows = [[s, d, b, p & 0xFFFFFFFF] for (p, s, d, b) in chunks]  # {src_off, dst_off, bytes, peer | pad<<32}
+    return torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
+
+
+@torch.no_grad()
+def make_plan(ctx: EPContext, selected_experts: torch.Tensor, num_experts: int, hidden: int) -> EPPlan:
+    """Routing + counts exchange + block lists (reference: preprocess, moe_layer.py:30-69)."""
+    ep, r = ctx.ep_size, ctx.rank
+    if num_experts % ep:
+        raise VB200Error("num_experts must be divisible by the EP group size")
+    el = num_experts // ep
+    T, K = selected_experts.shape
+    dev = selected_experts.device
+    splits, _cumsum, sidx = moe_route(selected_experts, num_experts)
+    # all-gather the per-expert counts through the symmetric region
+    cbuf = ctx.staging("counts", ep * num_experts * 4).view(torch.int32)[: ep * num_experts]
+    cbuf[r * num_experts : (r + 1) * num_experts].copy_(splits)
+    ctx.symm.all_gather_inplace(cbuf, num_experts, CH_EP_COUNTS, 1)
+    counts = cbuf.view(ep, num_experts).to("cpu", non_blocking=False).to(torch.int64)  # the one host sync
+    row = hidden * 2
+    excl = torch.cumsum(counts, dim=1) - counts  # [EP, E]: offset of expert e inside rank s's send order
+    input_splits = counts[r].view(ep, el).sum(dim=1).tolist()
+    mine = counts[:, r * el : (r + 1) * el]  # [EP, El]
+    output_splits = mine.sum(dim=1).tolist()
+    fwd, dst = [], 0
+    for le in range(el):
+        e = r * el + le
+        for s in range(ep):
+            n = int(counts[s, e])
+            if n:
+                fwd.append((s, int(excl[s, e]) * row, dst * row, n * row))
+            dst += n
+    total_recv = dst
+    cumsum_local = torch.cumsum(mine.sum(dim=0), dim=0).to(torch.int32).to(dev, non_blocking=True)
+    # return path: for every expert e (owner p), my block sits in p's output at
+    #   rows(sum_{le'<le} sum_s C[s, p*el+le']) + sum_{s<r} C[s, e]
+    bwd = []
+    per_expert_total = counts.sum(dim=0)  # [E]
+    for p in range(ep):
+        base = 0
+        for le in range(el):
+            e = p * el + le
+            n = int(counts[r, e])
+            if n:
+                src_row = base + int(counts[:r, e].sum())
+                bwd.append((p, src_row * row, int(excl[r, e]) * row, n * row))
+            base += int(per_expert_total[e])
+    return EPPlan(ctx, T, K, hidden, sidx, counts, input_splits, output_splits, total_recv, cumsum_local,
+                  _chunk_tensor(fwd, dev), len(fwd), _chunk_tensor(bwd, dev), len(bwd))
+
+
+def _pull(ctx: EPContext, channel: int, src_buf: torch.Tensor, chunks: torch.Tensor, n: int, out: torch.Tensor) -> None:
+    lib = _lib.load()
+    with torch.cuda.device(out.device):
+        check(lib.vb200_chunk_pull(ctx.symm.comm, channel, ctx.symm.offset_of(src_buf), chunks.data_ptr(), n,
+                                   out.data_ptr(), ctx.num_ctas, stream_ptr()), "vb200_chunk_pull")
+
+
+def _scatter_into(x: torch.Tensor, sidx: torch.Tensor, out: torch.Tensor, w: torch.Tensor | None = None) -> None:
+    """out[sidx[t,k]] = x[t] (optionally scaled by w[t,k], rounded to bf16)."""
+    T, K = sidx.shape
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        check(lib.vb200_moe_scatter(x.data_ptr(), sidx.data_ptr(), out.data_ptr(), w.data_ptr() if w is not None else None,
+                                    None, T, K, x.shape[-1], stream_ptr()), "vb200_moe_scatter")
+
+
+class _EPDispatch(torch.autograd.Function):
+    """token_pre_all2all (moe_layer.py:72-99): local permute -> exchange -> group by local expert."""
+
+    @staticmethod
+    def forward(ctx, hs, plan: EPPlan):
+        c = plan.ctx
+        send = c.staging("dispatch_send", plan.T * plan.K * plan.H * 2).view(BF)[: plan.T * plan.K * plan.H].view(-1, plan.H)
+        _scatter_into(hs.contiguous(), plan.sidx, send)
+        recv = torch.empty(max(plan.total_recv, 1), plan.H, dtype=BF, device=hs.device)[: plan.total_recv]
+        _pull(c, CH_EP_DISPATCH, send, plan.fwd_chunks, plan.n_fwd, recv)
+        ctx.plan = plan
+        return recv
+
+    @staticmethod
+    def backward(ctx, g):
+        plan: EPPlan = ctx.plan
+        c = plan.ctx
+        # gradients of received rows go back to their sources, then sum over the top-k slots
+        ret = c.staging("dispatch_grad", max(plan.total_recv, 1) * plan.H * 2).view(BF)[: plan.total_recv * plan.H].view(-1, plan.H)
+        ret.copy_(g)
+        back = torch.empty(plan.T * plan.K, plan.H, dtype=BF, device=g.device)
+        _pull(c, CH_EP_COMBINE, ret, plan.bwd_chunks, plan.n_bwd, back)
+        return _gather_raw(back, plan.sidx), None
+
+
+class _EPCombine(torch.autograd.Function):
+    """tokens_post_all2all (moe_layer.py:102-137): exchange back -> weight -> fp32 sum over the top-k."""
+
+    @staticmethod
+    def forward(ctx, expert_out, weights, plan: EPPlan):
+        c = plan.ctx
+        ret = c.staging("combine_ret", max(plan.total_recv, 1) * plan.H * 2).view(BF)[: plan.total_recv * plan.H].view(-1, plan.H)
+        ret.copy_(expert_out)
+        back = torch.empty(plan.T * plan.K, plan.H, dtype=BF, device=expert_out.device)
+        _pull(c, CH_EP_COMBINE, ret, plan.bwd_chunks, plan.n_bwd, back)
+        w = weights.to(BF).contiguous()
+        out = _gather_raw(back, plan.sidx, w)
+        ctx.plan = plan
+        ctx.save_for_backward(back, w)
+        ctx.w_dtype = weights.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan: EPPlan = ctx.plan
+        c = plan.ctx
+        back, w = ctx.saved_tensors
+        g = g.contiguous()
+        # d/d(expert_out): scatter w[t,k] * g[t] into the permuted order, owners pull their rows
+        send = c.staging("combine_grad", plan.T * plan.K * plan.H * 2).view(BF)[: plan.T * plan.K * plan.H].view(-1, plan.H)
+        _scatter_into(g, plan.sidx, send, w)
+        grad_expert = torch.empty(max(plan.total_recv, 1), plan.H, dtype=BF, device=g.device)[: plan.total_recv]
+        _pull(c, CH_EP_DISPATCH, send, plan.fwd_chunks, plan.n_fwd, grad_expert)
+        # d/d(weights)[t,k] = <g[t], back[sidx[t,k]]>
+        rows = back[plan.sidx.flatten().long()].view(plan.T, plan.K, plan.H)
+        grad_w = torch.einsum("th,tkh->tk", g.float(), rows.float()).to(ctx.w_dtype)
+        return grad_expert, grad_w, None
+
+
+class _EPExperts(torch.autograd.Function):
+    """EPMergedFc1GroupGemm (moe_layer.py:307-441): fc1 -> silu*up -> fc2 on the local experts, recompute in bwd."""
+
+    @staticmethod
+    def forward(ctx, tokens, cumsum, w1, w2):
+        inter = w1.shape[1] // 2
+        fc1 = group_gemm_same_nk(tokens, w1, cumsum, transpose_b=True)
+        with torch.no_grad():
+            act = F.silu_mul(fc1[:, :inter], fc1[:, inter:])
+        out = group_gemm_same_nk(act, w2, cumsum, transpose_b=True)
+        ctx.save_for_backward(tokens, cumsum, w1, w2, fc1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        tokens, cumsum, w1, w2, fc1 = ctx.saved_tensors
+        inter = w1.shape[1] // 2
+        g = g.contiguous()
+        with torch.no_grad():
+            act = F.silu_mul(fc1[:, :inter], fc1[:, inter:])  # recompute (moe_layer.py:389-391)
+        grad_act = group_gemm_same_nk(g, w2, cumsum, transpose_b=False)
+        grad_w2 = None
+        if ctx.needs_input_grad[3]:
+            grad_w2 = torch.empty_like(w2)
+            group_gemm_same_mn(g, act, grad_w2, cumsum)
+        grad_fc1 = torch.empty_like(fc1)
+        lib = _lib.load()
+        with torch.cuda.device(g.device):
+            check(lib.vb200_swiglu_bwd(grad_act.data_ptr(), fc1.data_ptr(), fc1.data_ptr() + inter * 2, grad_fc1.data_ptr(),
+                                       grad_fc1.data_ptr() + inter * 2, fc1.shape[0], inter, 2 * inter, inter, 2 * inter,
+                                       stream_ptr()), "vb200_swiglu_bwd")
+        grad_tokens = group_gemm_same_nk(grad_fc1, w1, cumsum, transpose_b=False)
+        grad_w1 = None
+        if ctx.needs_input_grad[2]:
+            grad_w1 = torch.empty_like(w1)
+            group_gemm_same_mn(grad_fc1, tokens, grad_w1, cumsum)
+        return grad_tokens, None, grad_w1, grad_w2
+
+
+def ep_dispatch(ctx: EPContext, hidden_states: torch.Tensor, selected_experts: torch.Tensor, num_experts: int):
+    """Returns (tokens [sum_recv, H] grouped by local expert, plan)."""
+    hs = hidden_states.reshape(-1, hidden_states.shape[-1])
+    plan = make_plan(ctx, selected_experts, num_experts, hs.shape[-1])
+    return _EPDispatch.apply(hs, plan), plan
+
+
+def ep_combine(expert_outputs: torch.Tensor, routing_weights: torch.Tensor, plan: EPPlan) -> torch.Tensor:
+    return _EPCombine.apply(expert_outputs, routing_weights, plan)
+
+
+def ep_fused_moe_forward(ctx: EPContext, num_experts: int, routing_weights, selected_experts, hidden_states,
+                         fc1_1_2_weight_local, fc2_weight_local):
+    """EP branch of the fused MoE forward; weights are this rank's ``[E/EP, ...]`` slices (ParallelPlan Shard(0))."""
+    shape = hidden_states.shape
+    tokens, plan = ep_dispatch(ctx, hidden_states, selected_experts, num_experts)
+    out = _EPExperts.apply(tokens, plan.cumsum_local, fc1_1_2_weight_local, fc2_weight_local)
+    return ep_combine(out, routing_weights, plan).reshape(shape)

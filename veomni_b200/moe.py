@@ -136,6 +136,8 @@ def group_gemm_same_nk(a: torch.Tensor, b: torch.Tensor, cumsum_M: torch.Tensor,
     if a.shape[1] != K or cumsum_M.numel() != G:
         raise VB200Error("group_gemm_same_nk: shape mismatch")
     c = torch.empty(a.shape[0], N, dtype=a.dtype, device=a.device)
+    if a.shape[0] == 0:
+        return c
     return _gg(0 if transpose_b else 1, a, b, c, _cumsum32(cumsum_M), G, a.shape[0], 0, N, K)
 
 
@@ -148,6 +150,8 @@ def group_gemm_same_mn(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, cumsum
     G, M, N = c.shape
     if a.shape[1] != M or b.shape[1] != N or a.shape[0] != b.shape[0] or not c.is_contiguous():
         raise VB200Error("group_gemm_same_mn: shape mismatch")
+    if a.shape[0] == 0:
+        return c.zero_()
     return _gg(2, a, b, c, _cumsum32(cumsum_K), G, a.shape[0], M, N, 0)
 
 
