@@ -40,3 +40,26 @@ def test_duplicate_registration_rejected():
         reg.register(spec)
     reg.register(spec, force=True)
     assert reg.resolve("op", "v", "x")() == 1
+
+
+def test_register_into_the_real_reference_when_present():
+    """In the authoring container the reference tree is importable: the b200 kernels land in ITS registry."""
+    import os
+    import sys
+
+    if not os.path.isdir("/root/reference/veomni"):
+        pytest.skip("reference tree not present (GPU box)")
+    sys.path.insert(0, "/root/reference")
+    try:
+        assert R.register() is True
+        from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
+        from veomni.ops.kernel_registry import KERNEL_REGISTRY as REF
+
+        for op, var in (("rms_norm", "standard"), ("rotary_pos_emb", "full"), ("swiglu_mlp", "standard"), ("moe_experts", "standard")):
+            assert "b200" in REF.list_available(op, var)
+        assert R.ATTN_NAME in ALL_ATTENTION_FUNCTIONS.valid_keys()
+        import veomni.distributed.sequence_parallel.ulysses as u
+
+        assert u.all_to_all_tensor.__module__ == "veomni_b200.ulysses"
+    finally:
+        sys.path.remove("/root/reference")
