@@ -1,0 +1,103 @@
+"""Host-side parallel logic on CPU: mesh layout (world_size-2 gloo), EP rank matrix, ParallelPlan slicing,
+symmetric-memory allocator bookkeeping."""
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from veomni_b200.parallel_plan import ParallelPlan, check_fqn_match, qwen3_moe_parallel_plan
+from veomni_b200.parallel_state import init_para_mesh_matrix
+
+
+def test_ep_rank_matrix_matches_reference_layout():
+    # reference init_para_mesh_matrix (parallel_state.py:50-73): EP ranks consecutive unless `outside`
+    assert init_para_mesh_matrix(2, 4).tolist() == [[0, 2, 4, 6], [1, 3, 5, 7]]
+    assert init_para_mesh_matrix(2, 4, para_outside=True).tolist() == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    assert init_para_mesh_matrix(8, 1).tolist() == [[r] for r in range(8)]
+
+
+def test_fqn_patterns():
+    assert check_fqn_match("model.layers.*.mlp.experts.gate_up_proj", "model.layers.17.mlp.experts.gate_up_proj")
+    assert not check_fqn_match("model.layers.*.mlp.experts.gate_up_proj", "model.layers.1.2.mlp.experts.gate_up_proj")
+    assert not check_fqn_match("model.layers.*.mlp.experts.down_proj", "model.layers.0.mlp.experts.gate_up_proj")
+
+
+def test_parallel_plan_slices_expert_weights():
+    class Experts(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_up_proj = torch.nn.Parameter(torch.arange(8 * 4 * 2, dtype=torch.float32).view(8, 4, 2))
+            self.down_proj = torch.nn.Parameter(torch.zeros(8, 2, 2))
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.Module()
+            layer = torch.nn.Module()
+            layer.mlp = torch.nn.Module()
+            layer.mlp.experts = Experts()
+            layer.norm = torch.nn.LayerNorm(2)
+            self.model.layers = torch.nn.ModuleList([layer])
+
+    m = M()
+    full = m.model.layers[0].mlp.experts.gate_up_proj.data.clone()
+    info = qwen3_moe_parallel_plan().apply(m, ep_size=4, ep_rank=2)
+    got = m.model.layers[0].mlp.experts.gate_up_proj
+    assert got.shape == (2, 4, 2) and torch.equal(got.data, full[4:6])
+    assert info["model.layers.0.mlp.experts.gate_up_proj"].placement.dim == 0
+    assert not hasattr(info["model.layers.0.norm.weight"].placement, "dim")  # Replicate
+    assert all(hasattr(p, "spec_info") for p in m.parameters())
+    with pytest.raises(AssertionError):
+        ParallelPlan({"ep": {"w": __import__("torch").distributed._tensor.Shard(0)}}).shard_tensor(torch.zeros(3, 2), "w", 2, 0)
+
+
+def _mesh_worker(rank, world, path, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    store = dist.FileStore(path, world)
+    dist.init_process_group("gloo", store=store, rank=rank, world_size=world)
+    from veomni_b200.parallel_state import init_parallel_state
+
+    ps = init_parallel_state(dp_size=1, ulysses_size=2, ep_size=2, device_type="cpu")
+    res = {
+        "fsdp_ranks": dist.get_process_group_ranks(ps.fsdp_group),
+        "ulysses_ranks": dist.get_process_group_ranks(ps.ulysses_group),
+        "ep_ranks": dist.get_process_group_ranks(ps.ep_group),
+        "sp": ps.sp_enabled, "ep": ps.ep_enabled, "div": ps.extra_parallel_gradient_divide_factor("ep"),
+    }
+    torch.save(res, os.path.join(out, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_parallel_state_mesh_world2_gloo():
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_mesh_worker, args=(2, os.path.join(d, "store"), d), nprocs=2, join=True)
+        for r in range(2):
+            res = torch.load(os.path.join(d, f"r{r}.pt"))
+            # Ulysses ranks are also FSDP shard ranks (parallel_state.py:87,95-96)
+            assert res["fsdp_ranks"] == [0, 1] and res["ulysses_ranks"] == [0, 1] and res["ep_ranks"] == [0, 1]
+            assert res["sp"] and res["ep"] and res["div"] == 2
+
+
+def test_symmetric_allocator_bookkeeping():
+    """First-fit free list with coalescing (pure host logic of veomni_b200.symm.Arena)."""
+    from veomni_b200._lib import VB200Error
+    from veomni_b200.symm import Arena
+
+    ar = Arena(1024, 4096)
+    a, sa = ar.alloc(1000)  # rounded up to 256-byte granules
+    b, sb = ar.alloc(1024)
+    c, sc = ar.alloc(2048)
+    assert (a, b, c) == (1024, 2048, 3072) and (sa, sb, sc) == (1024, 1024, 2048) and ar.free == []
+    with pytest.raises(VB200Error):
+        ar.alloc(1)
+    ar.release(b, sb)
+    ar.release(a, sa)
+    assert ar.free == [(1024, 2048)]  # coalesced
+    assert ar.alloc(2048)[0] == 1024
+    ar.release(1024, 2048)
+    ar.release(c, sc)
+    assert ar.free == [(1024, 4096)] and ar.live == 0

@@ -27,6 +27,40 @@ from ._lib import VB200Error, check
 _ALIGN = 256
 
 
+class Arena:
+    """First-fit free list with coalescing over [base, base + size). Pure host bookkeeping."""
+
+    def __init__(self, base: int, size: int):
+        self.base, self.size = base, size
+        self.free: list[tuple[int, int]] = [(base, size)]
+        self.live = 0
+
+    def alloc(self, nbytes: int) -> tuple[int, int]:
+        size = max(_ALIGN, (int(nbytes) + _ALIGN - 1) // _ALIGN * _ALIGN)
+        for i, (o, s) in enumerate(self.free):
+            if s >= size:
+                if s == size:
+                    self.free.pop(i)
+                else:
+                    self.free[i] = (o + size, s - size)
+                self.live += size
+                return o, size
+        raise VB200Error(f"symmetric arena exhausted: need {size} B of {self.size} B (live {self.live} B); "
+                         "raise the region size passed to SymmetricMemory")
+
+    def release(self, off: int, size: int) -> None:
+        self.live -= size
+        fl = sorted(self.free + [(off, size)])
+        merged = [fl[0]]
+        for o, s in fl[1:]:
+            lo, ls = merged[-1]
+            if lo + ls == o:
+                merged[-1] = (lo, ls + s)
+            else:
+                merged.append((o, s))
+        self.free = merged
+
+
 class _Block:
     """Lifetime anchor of one allocation: torch keeps it alive as long as the storage lives."""
 
@@ -81,8 +115,7 @@ class SymmetricMemory:
         # Arenas: independent first-fit free lists over disjoint slices of the data region. A block is
         # only ever reused by the same class of user (FSDP all-gather outputs / reduce-scatter inputs /
         # everything else), whose own stream protocol makes same-class reuse safe.
-        self._arenas: dict[str, list[tuple[int, int]]] = {}
-        self._arena_bounds: dict[str, tuple[int, int]] = {}
+        self._arenas: dict[str, Arena] = {}
         arenas = arenas or {"misc": 1.0}
         tot = float(sum(arenas.values()))
         cur = 0
@@ -91,48 +124,19 @@ class SymmetricMemory:
             size = int(self.data_bytes * (arenas[name] / tot)) // _ALIGN * _ALIGN
             if i == len(names) - 1:
                 size = self.data_bytes - cur
-            self._arenas[name] = [(cur, size)]
-            self._arena_bounds[name] = (cur, size)
+            self._arenas[name] = Arena(cur, size)
             cur += size
-        self._live = 0
         dist.barrier(group=self.group)  # every peer has mapped every region before first use
 
     # ---- allocation ---------------------------------------------------------------------------
-    def _release(self, arena: str, off: int, size: int) -> None:
-        self._live -= size
-        fl = self._arenas[arena]
-        fl.append((off, size))
-        fl.sort()
-        merged = [fl[0]]
-        for o, s in fl[1:]:
-            lo, ls = merged[-1]
-            if lo + ls == o:
-                merged[-1] = (lo, ls + s)
-            else:
-                merged.append((o, s))
-        self._arenas[arena] = merged
-
     def alloc(self, nbytes: int, arena: str = "misc") -> tuple[int, torch.Tensor]:
         """Return (offset, uint8 tensor) of a block in the local data region; freed with the tensor."""
-        size = max(_ALIGN, (int(nbytes) + _ALIGN - 1) // _ALIGN * _ALIGN)
         if arena not in self._arenas:
             arena = "misc" if "misc" in self._arenas else next(iter(self._arenas))
-        fl = self._arenas[arena]
-        for i, (o, s) in enumerate(fl):
-            if s >= size:
-                if s == size:
-                    fl.pop(i)
-                else:
-                    fl[i] = (o + size, s - size)
-                break
-        else:
-            raise VB200Error(
-                f"symmetric arena '{arena}' exhausted: need {size} B of {self._arena_bounds[arena][1]} B "
-                f"(free list {fl[:4]}...); raise the region size passed to SymmetricMemory"
-            )
-        self._live += size
+        ar = self._arenas[arena]
+        o, size = ar.alloc(nbytes)
         block = _Block(self.data_ptr + o, int(nbytes))
-        weakref.finalize(block, self._release, arena, o, size)
+        weakref.finalize(block, ar.release, o, size)
         t = torch.as_tensor(block, device=self.device)
         return o, t
 
