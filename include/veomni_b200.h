@@ -108,6 +108,12 @@ int vb200_attn_varlen_fwd(const void* q, const void* k, const void* v, void* o, 
                           const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,
                           int32_t q_heads, int32_t k_heads, int32_t head_dim, const int64_t* strides,
                           float scale, int32_t causal, void* stream);
+/* Same contract as vb200_attn_varlen_fwd for head_dim == 128, on the tcgen05 tensor cores (TMEM-resident
+ * S and PV tiles, softmax warps on tcgen05.ld).                                                   */
+int vb200_attn_varlen_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse,
+                             const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,
+                             int32_t q_heads, int32_t k_heads, int32_t head_dim, const int64_t* strides,
+                             float scale, int32_t causal, void* stream);
 int vb200_attn_varlen_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                           const float* lse, float* delta, void* dq, void* dk, void* dv,
                           const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,

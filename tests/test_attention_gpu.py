@@ -120,3 +120,45 @@ def test_attention_full_size_qwen3_8b_shape(cuda_dev):
     cu2 = torch.tensor([0, 1000], dtype=torch.int32).to(cuda_dev)
     o_short = flash_attn_varlen(q[:1000].to(cuda_dev), k[:1000].to(cuda_dev), v[:1000].to(cuda_dev), cu2, 1000)
     torch.testing.assert_close(o_short.float(), o1[:1000].float(), atol=1e-2, rtol=1e-2)
+
+
+@pytest.fixture
+def tc_forward():
+    from veomni_b200 import attention as A
+
+    old = A.FWD_IMPL
+    A.FWD_IMPL = "tc"
+    yield
+    A.FWD_IMPL = old
+
+
+@pytest.mark.parametrize("lens", [[1], [64], [127], [128], [129], [1, 63, 64, 65, 127, 129, 300], [257, 3, 511], [1000, 24]])
+def test_attention_tcgen05_forward_ragged(cuda_dev, tc_forward, lens):
+    """tcgen05/TMEM forward (attention_tc.cu) against the oracle; backward runs on its saved o/lse."""
+    _run(cuda_dev, lens, Hq=4, Hk=2, D=128, seed=len(lens) + 7)
+
+
+def test_attention_tcgen05_forward_gqa_noncausal(cuda_dev, tc_forward):
+    _run(cuda_dev, [200, 333], 8, 2, 128, seed=3)
+    _run(cuda_dev, [100, 260], 4, 4, 128, seed=4, causal=False)
+
+
+def test_attention_tcgen05_matches_mma_at_full_size(cuda_dev):
+    from veomni_b200 import attention as A
+
+    g = torch.Generator().manual_seed(9)
+    T, Hq, Hk, D = 4096, 32, 8, 128
+    q, k, v = (torch.randn(T, h, D, generator=g).to(BF).to(cuda_dev) for h in (Hq, Hk, Hk))
+    cu = torch.tensor([0, 1500, T], dtype=torch.int32, device=cuda_dev)
+    old = A.FWD_IMPL
+    try:
+        A.FWD_IMPL = "mma"
+        o1, l1 = A.flash_attn_varlen(q, k, v, cu, 2596, return_lse=True)
+        A.FWD_IMPL = "tc"
+        o2, l2 = A.flash_attn_varlen(q, k, v, cu, 2596, return_lse=True)
+        o3, _ = A.flash_attn_varlen(q, k, v, cu, 2596, return_lse=True)
+    finally:
+        A.FWD_IMPL = old
+    assert torch.equal(o2, o3), "tcgen05 forward must be deterministic"
+    torch.testing.assert_close(o2.float(), o1.float(), atol=1e-2, rtol=2e-2)
+    torch.testing.assert_close(l2, l1, atol=2e-3, rtol=1e-4)

@@ -16,6 +16,17 @@ def bench_attention(dev, iters):
     with torch.no_grad():
         report("attn_fwd[4096,32/8,128,causal]", time_fn(lambda q, k, v: flash_attn_varlen(q, k, v, cu, T), sets, iters),
                flops=flops_fwd)
+    from veomni_b200 import attention as A
+
+    old = A.FWD_IMPL
+    A.FWD_IMPL = "tc"
+    try:
+        with torch.no_grad():
+            report("attn_fwd_tcgen05[4096,32/8,128,causal]", time_fn(lambda q, k, v: flash_attn_varlen(q, k, v, cu, T), sets, iters),
+                   flops=flops_fwd)
+    except Exception as ex:  # noqa: BLE001
+        print({"attn_fwd_tcgen05": str(ex)})
+    A.FWD_IMPL = old
     gsets = [tuple(t.clone().requires_grad_(True) for t in s) for s in sets]
     do = torch.randn(T, Hq, D, device=dev, dtype=BF)
 

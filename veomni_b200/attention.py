@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
 
@@ -16,6 +17,9 @@ from ._lib import VB200Error, check, stream_ptr
 # When set to a list, every forward launch appends a (start, end) CUDA-event pair recorded on the
 # launching stream (bench.py uses it for the live per-launch duration of the dominant kernel).
 PROFILE = None
+
+# Forward implementation for head_dim 128: "tc" = tcgen05/TMEM pipeline (attention_tc.cu), "mma" = mma.sync kernel.
+FWD_IMPL = os.environ.get("VB200_ATTN_FWD", "mma")
 
 
 def _strides(*tensors):
@@ -36,7 +40,7 @@ def _prep(t: torch.Tensor) -> torch.Tensor:
 
 class _VarlenAttn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, cu_seqlens, max_seqlen, scale, causal):
+    def forward(ctx, q, k, v, cu_seqlens, max_seqlen, scale, causal, replay=None):
         for t in (q, k, v):
             if not t.is_cuda or t.dtype != torch.bfloat16:
                 raise VB200Error("veomni_b200 attention expects CUDA bfloat16 q/k/v (no CPU fallback)")
@@ -45,18 +49,25 @@ class _VarlenAttn(torch.autograd.Function):
         Hk = k.shape[1]
         cu = cu_seqlens.to(device=q.device, dtype=torch.int32).contiguous()
         nseq = cu.numel() - 1
+        scale = float(scale) if scale is not None else 1.0 / math.sqrt(D)
+        if replay is not None:
+            # gradient-checkpoint recompute: the kernel is deterministic, so the (o, lse) kept from the first
+            # forward ARE what a relaunch would produce — keep them resident instead of recomputing.
+            o, lse = replay
+            ctx.save_for_backward(q, k, v, o, lse, cu)
+            ctx.meta = (int(max_seqlen), scale, bool(causal))
+            return o
         o = torch.empty(T, Hq, D, dtype=q.dtype, device=q.device)
         lse = torch.empty(Hq, T, dtype=torch.float32, device=q.device)
-        scale = float(scale) if scale is not None else 1.0 / math.sqrt(D)
         lib = _lib.load()
         with torch.cuda.device(q.device):
             if PROFILE is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            fwd = lib.vb200_attn_varlen_fwd_tc if (FWD_IMPL == "tc" and D == 128) else lib.vb200_attn_varlen_fwd
             check(
-                lib.vb200_attn_varlen_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
-                                          cu.data_ptr(), nseq, int(max_seqlen), T, Hq, Hk, D, _strides(q, k, v, o),
-                                          scale, 1 if causal else 0, stream_ptr()),
+                fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), cu.data_ptr(), nseq,
+                    int(max_seqlen), T, Hq, Hk, D, _strides(q, k, v, o), scale, 1 if causal else 0, stream_ptr()),
                 "vb200_attn_varlen_fwd",
             )
             if PROFILE is not None:
@@ -65,10 +76,11 @@ class _VarlenAttn(torch.autograd.Function):
                 PROFILE.append((ev0, ev1))
         ctx.save_for_backward(q, k, v, o, lse, cu)
         ctx.meta = (int(max_seqlen), scale, bool(causal))
-        return o
+        ctx.mark_non_differentiable(lse)
+        return o, lse
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, _dlse=None):
         q, k, v, o, lse, cu = ctx.saved_tensors
         max_seqlen, scale, causal = ctx.meta
         dout = _prep(dout)
@@ -88,12 +100,18 @@ class _VarlenAttn(torch.autograd.Function):
                                           stream_ptr()),
                 "vb200_attn_varlen_bwd",
             )
-        return dq, dk, dv, None, None, None, None
+        return dq, dk, dv, None, None, None, None, None
 
 
-def flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen: int, softmax_scale: float | None = None, causal: bool = True):
-    """q ``[T,Hq,D]``, k/v ``[T,Hkv,D]`` packed bf16; ``cu_seqlens`` int32 ``[nseq+1]``. Returns ``[T,Hq,D]``."""
-    return _VarlenAttn.apply(q, k, v, cu_seqlens, max_seqlen, softmax_scale, causal)
+def flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen: int, softmax_scale: float | None = None, causal: bool = True,
+                      return_lse: bool = False, replay=None):
+    """q ``[T,Hq,D]``, k/v ``[T,Hkv,D]`` packed bf16; ``cu_seqlens`` int32 ``[nseq+1]``. Returns ``[T,Hq,D]``
+    (and the fp32 log-sum-exp ``[Hq,T]`` with ``return_lse``).  ``replay=(o, lse)`` re-attaches a previously computed
+    result to the autograd graph without relaunching the forward kernel (checkpoint recompute)."""
+    out = _VarlenAttn.apply(q, k, v, cu_seqlens, max_seqlen, softmax_scale, causal, replay)
+    if replay is not None:
+        return (out, replay[1]) if return_lse else out
+    return out if return_lse else out[0]
 
 
 def flash_attention_forward(module, query, key, value, attention_mask, dropout: float = 0.0, scaling: float | None = None,

@@ -1,0 +1,301 @@
+// Packed varlen causal attention FORWARD on the 5th-generation tensor cores (tcgen05 + TMEM), head_dim 128.
+//
+// Same contract as attn_fwd_kernel in attention.cu (reference call site: flash_attn_varlen_func behind
+// veomni/ops/kernels/attention/__init__.py:304-320); this is the Blackwell-native pipeline:
+//
+//   warp 0      TMA producer   Q once; K_j / V_j tiles (128 kv rows) into 2-stage smem rings (SWIZZLE_128B boxes)
+//   warp 1      MMA issuer     S_j  = Q K_j^T   tcgen05.mma M128 N128 K16 x8, K-major A/B      -> TMEM S[j&1]
+//                              OT_j = P_j V_j   tcgen05.mma, A = P (smem, K-major), B = V (MN-major) -> TMEM OT[j&1]
+//                              (S_{j+1} is issued before PV_j so the tensor pipe runs ahead of the softmax)
+//   warps 2..5  softmax        thread == query row (TMEM lane): pass 1 row max from tcgen05.ld, pass 2 exp2 -> bf16 P
+//                              written to swizzled smem; O accumulates in registers: O = alpha*O + OT (no TMEM
+//                              read-modify-write correction pass); LSE saved for the backward
+// TMEM: 512 columns = S[2] (2x128) + OT[2] (2x128).  smem: Q 32 KB + K 2x32 KB + V 2x32 KB + P 32 KB.
+// All hand-offs are mbarriers (TMA tx-count, tcgen05.commit, thread arrives) — no __syncthreads in the loop.
+#include "umma.cuh"
+
+namespace vb {
+
+struct AttnTcParams {
+    const int* cu_seqlens;
+    int Hq, Hk, total;
+    float scale;
+    int causal;
+    __nv_bfloat16* o;
+    int64_t o_stride_tok, o_stride_head;
+    float* lse;
+};
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_D = 128;
+constexpr int TC_TILE = TC_BM * TC_D * 2;  // 32 KB
+constexpr float kLog2eTc = 1.4426950408889634f;
+
+enum {  // barrier indices
+    B_Q = 0, B_KFULL = 1, B_VFULL = 3, B_KEMPTY = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11, B_PFULL = 13,
+    B_PEMPTY = 14, B_OFULL = 15, B_OEMPTY = 17, B_COUNT = 19
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TC_TILE;          // 2 stages
+    uint8_t* sV = sK + 2 * TC_TILE;      // 2 stages
+    uint8_t* sP = sV + 2 * TC_TILE;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sP + TC_TILE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int seq = blockIdx.z, h = blockIdx.y;
+    const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
+    const int mblk = (int)gridDim.x - 1 - (int)blockIdx.x;
+    const int m0 = mblk * TC_BM;
+    if (m0 >= L) return;
+    const int hk = h / (p.Hq / p.Hk);
+    const int kv_end = p.causal ? min(L, m0 + TC_BM) : L;
+    const int n_tiles = (kv_end + TC_BN - 1) / TC_BN;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < B_COUNT; ++i) {
+            const bool by_warps = (i >= B_SEMPTY && i < B_SEMPTY + 2) || i == B_PFULL || (i >= B_OEMPTY && i < B_OEMPTY + 2);
+            mbar_init(&bar[i], by_warps ? 4 : 1);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            mbar_expect_tx(&bar[B_Q], TC_TILE);
+            tma_load_3d(sQ, &tmQ, 0, h, s0 + m0, &bar[B_Q]);
+            tma_load_3d(sQ + TC_BM * 128, &tmQ, 64, h, s0 + m0, &bar[B_Q]);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(&bar[B_KEMPTY + st], ph ^ 1);
+                mbar_expect_tx(&bar[B_KFULL + st], TC_TILE);
+                tma_load_3d(sK + st * TC_TILE, &tmK, 0, hk, s0 + j * TC_BN, &bar[B_KFULL + st]);
+                tma_load_3d(sK + st * TC_TILE + TC_BN * 128, &tmK, 64, hk, s0 + j * TC_BN, &bar[B_KFULL + st]);
+                mbar_wait(&bar[B_VEMPTY + st], ph ^ 1);
+                mbar_expect_tx(&bar[B_VFULL + st], TC_TILE);
+                tma_load_3d(sV + st * TC_TILE, &tmV, 0, hk, s0 + j * TC_BN, &bar[B_VFULL + st]);
+                tma_load_3d(sV + st * TC_TILE + TC_BN * 128, &tmV, 64, hk, s0 + j * TC_BN, &bar[B_VFULL + st]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc_qk = umma_idesc(0, 0, TC_BM, TC_BN);  // A, B K-major
+        constexpr uint32_t idesc_pv = umma_idesc(0, 1, TC_BM, TC_D);   // A K-major (P), B MN-major (V)
+        const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+        mbar_wait(&bar[B_Q], 0);
+        for (int j = 0; j <= n_tiles; ++j) {
+            if (j < n_tiles) {  // S_j = Q K_j^T
+                const int st = j & 1;
+                const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(&bar[B_SEMPTY + st], ph ^ 1);
+                mbar_wait(&bar[B_KFULL + st], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t k_addr = smem_u32(sK + st * TC_TILE);
+#pragma unroll
+                    for (int k = 0; k < TC_D / 16; ++k) {
+                        const uint32_t off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16(tmem + st * TC_BN, umma_desc(q_addr + off, 16, 1024), umma_desc(k_addr + off, 16, 1024),
+                                 idesc_qk, k ? 1u : 0u);
+                    }
+                    umma_commit(&bar[B_KEMPTY + st]);
+                    umma_commit(&bar[B_SFULL + st]);
+                }
+                __syncwarp();
+            }
+            if (j >= 1) {  // OT_{j-1} = P_{j-1} V_{j-1}
+                const int i = j - 1, st = i & 1;
+                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                mbar_wait(&bar[B_OEMPTY + st], ph ^ 1);
+                mbar_wait(&bar[B_VFULL + st], ph);
+                mbar_wait(&bar[B_PFULL], (uint32_t)i & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t v_addr = smem_u32(sV + st * TC_TILE);
+#pragma unroll
+                    for (int k = 0; k < TC_BN / 16; ++k) {
+                        const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16(tmem + 256 + st * TC_D, umma_desc(p_addr + a_off, 16, 1024),
+                                 umma_desc(v_addr + k * 16 * 128, TC_BN * 128, 1024), idesc_pv, k ? 1u : 0u);
+                    }
+                    umma_commit(&bar[B_VEMPTY + st]);
+                    umma_commit(&bar[B_PEMPTY]);
+                    umma_commit(&bar[B_OFULL + st]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== softmax + output accumulation: thread == query row =====
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int m = m0 + r;  // sequence-relative query index
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        const float sl2 = p.scale * kLog2eTc;
+        float o_acc[TC_D];
+#pragma unroll
+        for (int i = 0; i < TC_D; ++i) o_acc[i] = 0.f;
+        float m_i = -INFINITY, l_i = 0.f, alpha_lag = 1.f;
+        const uint32_t sP_a = smem_u32(sP);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j & 1;
+            const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+            mbar_wait(&bar[B_SFULL + st], ph);
+            tc_fence_after();
+            const bool need_mask = (j * TC_BN + TC_BN > L) || (p.causal && j * TC_BN + TC_BN > m0);
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + st * TC_BN + c * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float s = __uint_as_float(v[i]);
+                    if (need_mask) {
+                        const int n = j * TC_BN + c * 32 + i;
+                        if (n >= L || (p.causal && n > m)) s = -INFINITY;
+                    }
+                    mx = fmaxf(mx, s);
+                }
+            }
+            const float m_new = fmaxf(m_i, mx);
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+            const float alpha = exp2f((m_i - m_use) * sl2);
+            m_i = m_new;
+            // the P buffer is free once PV_{j-1} has been committed
+            if (j >= 1) mbar_wait(&bar[B_PEMPTY], (uint32_t)(j - 1) & 1u);
+            // pass 2: P = exp2(S*sl2 - m*sl2) -> bf16, swizzled K-major smem tile; row sum
+            float sum = 0.f;
+            const float mb = m_use * sl2;
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + st * TC_BN + c * 32, v);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float e0 = exp2f(__uint_as_float(v[i]) * sl2 - mb), e1 = exp2f(__uint_as_float(v[i + 1]) * sl2 - mb);
+                    if (need_mask) {
+                        const int n = j * TC_BN + c * 32 + i;
+                        if (n >= L || (p.causal && n > m)) e0 = 0.f;
+                        if (n + 1 >= L || (p.causal && n + 1 > m)) e1 = 0.f;
+                    }
+                    sum += e0 + e1;
+                    pk[i >> 1] = f2_to_bf2(e0, e1);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {  // 4 x 16-byte chunks = 32 columns
+                    const int chunk = c * 4 + g;  // 0..15 over the 128 kv columns
+                    const uint32_t addr = swz_addr(sP_a, TC_BM, r, chunk);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                                 "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
+                }
+            }
+            l_i = l_i * alpha + sum;
+            tc_fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bar[B_SEMPTY + st]);
+                mbar_arrive(&bar[B_PFULL]);
+            }
+            // fold in OT_{j-1}
+            if (j >= 1) {
+                const int ost = (j - 1) & 1;
+                mbar_wait(&bar[B_OFULL + ost], (uint32_t)((j - 1) >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < TC_D / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + 256 + ost * TC_D + c * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_lag, __uint_as_float(v[i]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar[B_OEMPTY + ost]);
+            }
+            alpha_lag = alpha;
+        }
+        {   // last tile's OT
+            const int ost = (n_tiles - 1) & 1;
+            mbar_wait(&bar[B_OFULL + ost], (uint32_t)((n_tiles - 1) >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < TC_D / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + 256 + ost * TC_D + c * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_lag, __uint_as_float(v[i]));
+            }
+            tc_fence_before();
+        }
+        if (m < L) {
+            const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
+            p.lse[(int64_t)h * p.total + s0 + m] = (l_i > 0.f) ? m_i * p.scale + logf(l_i) : -INFINITY;
+            __nv_bfloat16* orow = p.o + (int64_t)(s0 + m) * p.o_stride_tok + (int64_t)h * p.o_stride_head;
+#pragma unroll
+            for (int c = 0; c < TC_D / 8; ++c) {
+                uint4 w;
+                w.x = f2_to_bf2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+                w.y = f2_to_bf2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+                w.z = f2_to_bf2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+                w.w = f2_to_bf2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+                *reinterpret_cast<uint4*>(orow + c * 8) = w;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" int vb200_attn_varlen_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse,
+                                        const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,
+                                        int32_t q_heads, int32_t k_heads, int32_t head_dim, const int64_t* st, float scale,
+                                        int32_t causal, void* stream) {
+    if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_fwd_tc: head_dim must be 128");
+    if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_fwd_tc: Hq % Hk != 0");
+    for (int i = 0; i < 8; ++i)
+        if (st[i] & 7) return vb200_set_error(VB200_EINVAL, "attn_fwd_tc: strides must be multiples of 8 elements");
+    if (total <= 0 || num_seqs <= 0 || max_seqlen <= 0) return VB200_OK;
+    CUtensorMap tmQ, tmK, tmV;
+    int rc;
+    if ((rc = make_tmap_3d(&tmQ, q, 128, q_heads, total, st[1], st[0], 128))) return rc;
+    if ((rc = make_tmap_3d(&tmK, k, 128, k_heads, total, st[3], st[2], 128))) return rc;
+    if ((rc = make_tmap_3d(&tmV, v, 128, k_heads, total, st[5], st[4], 128))) return rc;
+    AttnTcParams p{};
+    p.cu_seqlens = cu_seqlens; p.Hq = q_heads; p.Hk = k_heads; p.total = total; p.scale = scale; p.causal = causal;
+    p.o = (__nv_bfloat16*)o; p.o_stride_tok = st[6]; p.o_stride_head = st[7]; p.lse = lse;
+    const size_t smem = 6 * TC_TILE + B_COUNT * 8 + 16 + 64;
+    static bool attr = false;
+    if (!attr) {
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid((max_seqlen + TC_BM - 1) / TC_BM, q_heads, num_seqs);
+    attn_fwd_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}

@@ -101,6 +101,10 @@ class Qwen3Attention(nn.Module):
         self.q_norm = Qwen3RMSNorm(D, cfg.rms_norm_eps)
         self.k_norm = Qwen3RMSNorm(D, cfg.rms_norm_eps)
         self.scaling = D**-0.5
+        # gradient checkpointing: (forward id, o, lse) of the first forward, consumed by the recompute
+        self.keep_attention = False
+        self._fwd_id = 0
+        self._stash = None
 
     def forward(self, x, cos, sin, cu_seqlens, max_seqlen, sp_group=None):
         # x: [T_local, hidden]; cos/sin: [T_local, D]
@@ -119,7 +123,14 @@ class Qwen3Attention(nn.Module):
                 k = torch.repeat_interleave(k, P // cfg.num_key_value_heads, dim=1)
                 v = torch.repeat_interleave(v, P // cfg.num_key_value_heads, dim=1)
             q, k, v = U.gather_seq_scatter_heads_qkv(q, k, v, seq_dim=0, head_dim=1, group=sp_group)
-        o = flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen, self.scaling, True)
+        st = self._stash
+        if self.keep_attention and torch.is_grad_enabled() and st is not None and st[0] == self._fwd_id:
+            self._stash = None  # recompute pass: reuse the deterministic result instead of relaunching
+            o = flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen, self.scaling, True, replay=(st[1], st[2]))
+        else:
+            o, lse = flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen, self.scaling, True, return_lse=True)
+            if self.keep_attention and self.training and torch.is_grad_enabled():
+                self._stash = (self._fwd_id, o.detach(), lse)
         if sp_group is not None:
             o = U.gather_heads_scatter_seq(o, head_dim=1, seq_dim=0, group=sp_group)
         return self.o_proj(o.reshape(T, -1))
@@ -157,6 +168,8 @@ class Qwen3ForCausalLM(nn.Module):
         if cfg.tie_word_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
         self.gradient_checkpointing = False
+        self.keep_attention_in_checkpoint = True  # keep (o, lse) resident instead of recomputing attention
+        self._fwd_counter = 0
         self.sp_group = None
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float() / cfg.head_dim))
         self.register_buffer("inv_freq", inv, persistent=False)
@@ -189,8 +202,12 @@ class Qwen3ForCausalLM(nn.Module):
         """
         h = self.model.embed_tokens(input_ids.reshape(-1))
         cos, sin = self.rotary(position_ids, h.dtype)
+        self._fwd_counter += 1
+        ckpt = self.gradient_checkpointing and self.training
         for layer in self.model.layers:
-            if self.gradient_checkpointing and self.training:
+            layer.self_attn.keep_attention = ckpt and self.keep_attention_in_checkpoint
+            layer.self_attn._fwd_id = self._fwd_counter
+            if ckpt:
                 h = checkpoint(layer, h, cos, sin, cu_seqlens, max_seqlen, self.sp_group, use_reentrant=False)
             else:
                 h = layer(h, cos, sin, cu_seqlens, max_seqlen, self.sp_group)
