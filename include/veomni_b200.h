@@ -114,6 +114,15 @@ int vb200_attn_varlen_fwd_tc(const void* q, const void* k, const void* v, void* 
                              const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,
                              int32_t q_heads, int32_t k_heads, int32_t head_dim, const int64_t* strides,
                              float scale, int32_t causal, void* stream);
+/* tcgen05 backward (head_dim 128): delta = rowsum(dO*O) first, then dq / dk / dv. strides: (token, head)
+ * element strides of q, k, v, dout, dq, dk, dv (14 values). Deterministic (no atomics).           */
+int vb200_attn_bwd_delta(const void* o, const void* dout, float* delta, int32_t total, int32_t q_heads,
+                         int32_t head_dim, int64_t o_stride_tok, int64_t o_stride_head, int64_t do_stride_tok,
+                         int64_t do_stride_head, void* stream);
+int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                             const float* delta, void* dq, void* dk, void* dv, const int32_t* cu_seqlens,
+                             int32_t num_seqs, int32_t max_seqlen, int32_t total, int32_t q_heads, int32_t k_heads,
+                             int32_t head_dim, const int64_t* strides, float scale, int32_t causal, void* stream);
 int vb200_attn_varlen_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                           const float* lse, float* delta, void* dq, void* dk, void* dv,
                           const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,

@@ -162,3 +162,48 @@ def test_attention_tcgen05_matches_mma_at_full_size(cuda_dev):
     assert torch.equal(o2, o3), "tcgen05 forward must be deterministic"
     torch.testing.assert_close(o2.float(), o1.float(), atol=1e-2, rtol=2e-2)
     torch.testing.assert_close(l2, l1, atol=2e-3, rtol=1e-4)
+
+
+@pytest.fixture
+def tc_backward():
+    from veomni_b200 import attention as A
+
+    old = (A.FWD_IMPL, A.BWD_IMPL)
+    A.FWD_IMPL, A.BWD_IMPL = "tc", "tc"
+    yield
+    A.FWD_IMPL, A.BWD_IMPL = old
+
+
+@pytest.mark.parametrize("lens", [[1], [64], [65], [127], [128], [129], [1, 63, 64, 65, 127, 129, 300], [257, 3, 511], [1000, 24]])
+def test_attention_tcgen05_backward_ragged(cuda_dev, tc_backward, lens):
+    _run(cuda_dev, lens, Hq=4, Hk=2, D=128, seed=len(lens) + 11)
+
+
+def test_attention_tcgen05_backward_gqa_noncausal(cuda_dev, tc_backward):
+    _run(cuda_dev, [200, 333], 8, 2, 128, seed=13)
+    _run(cuda_dev, [200, 333], 6, 1, 128, seed=14)
+    _run(cuda_dev, [100, 260], 4, 4, 128, seed=15, causal=False)
+
+
+def test_attention_tcgen05_backward_matches_mma_full_size(cuda_dev):
+    from veomni_b200 import attention as A
+
+    g = torch.Generator().manual_seed(21)
+    T, Hq, Hk, D = 4096, 32, 8, 128
+    q, k, v, do = (torch.randn(T, h, D, generator=g).to(BF).to(cuda_dev) for h in (Hq, Hk, Hk, Hq))
+    cu = torch.tensor([0, T], dtype=torch.int32, device=cuda_dev)
+    res = {}
+    old = (A.FWD_IMPL, A.BWD_IMPL)
+    try:
+        for impl in ("mma", "tc", "tc2"):
+            A.FWD_IMPL = A.BWD_IMPL = "tc" if impl.startswith("tc") else "mma"
+            qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+            A.flash_attn_varlen(qq, kk, vv, cu, T).backward(do)
+            res[impl] = (qq.grad, kk.grad, vv.grad)
+    finally:
+        A.FWD_IMPL, A.BWD_IMPL = old
+    for a, b in zip(res["tc"], res["tc2"]):
+        assert torch.equal(a, b), "tcgen05 backward must be deterministic"
+    for name, a, b in zip(("dq", "dk", "dv"), res["tc"], res["mma"]):
+        s = max(1.0, float(b.float().abs().max()))
+        torch.testing.assert_close(a.float() / s, b.float() / s, atol=1e-2, rtol=2e-2, msg=lambda m, n=name: f"{n}: {m}")

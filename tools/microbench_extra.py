@@ -36,6 +36,13 @@ def bench_attention(dev, iters):
         q.grad = k.grad = v.grad = None
 
     report("attn_fwd+bwd[4096,32/8,128,causal]", time_fn(fb, gsets, iters), flops=flops_fwd * 3.5)
+    old2 = (A.FWD_IMPL, A.BWD_IMPL)
+    A.FWD_IMPL = A.BWD_IMPL = "tc"
+    try:
+        report("attn_fwd+bwd_tcgen05[4096,32/8,128,causal]", time_fn(fb, gsets, iters), flops=flops_fwd * 3.5)
+    except Exception as ex:  # noqa: BLE001
+        print({"attn_bwd_tcgen05": str(ex)})
+    A.FWD_IMPL, A.BWD_IMPL = old2
     try:
         from flash_attn import flash_attn_varlen_func
 

@@ -20,6 +20,7 @@ PROFILE = None
 
 # Forward implementation for head_dim 128: "tc" = tcgen05/TMEM pipeline (attention_tc.cu), "mma" = mma.sync kernel.
 FWD_IMPL = os.environ.get("VB200_ATTN_FWD", "mma")
+BWD_IMPL = os.environ.get("VB200_ATTN_BWD", "mma")
 
 
 def _strides(*tensors):
@@ -91,6 +92,16 @@ class _VarlenAttn(torch.autograd.Function):
             dq, dk, dv = (torch.empty(t.shape, dtype=t.dtype, device=t.device) for t in (q, k, v))
         delta = torch.empty(Hq, T, dtype=torch.float32, device=q.device)
         lib = _lib.load()
+        if BWD_IMPL == "tc" and D == 128:
+            with torch.cuda.device(q.device):
+                check(lib.vb200_attn_bwd_delta(o.data_ptr(), dout.data_ptr(), delta.data_ptr(), T, Hq, D, o.stride(0), o.stride(1),
+                                               dout.stride(0), dout.stride(1), stream_ptr()), "vb200_attn_bwd_delta")
+                check(lib.vb200_attn_varlen_bwd_tc(q.data_ptr(), k.data_ptr(), v.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                                   delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), cu.data_ptr(),
+                                                   cu.numel() - 1, max_seqlen, T, Hq, Hk, D,
+                                                   _strides(q, k, v, dout, dq, dk, dv), scale, 1 if causal else 0,
+                                                   stream_ptr()), "vb200_attn_varlen_bwd_tc")
+            return dq, dk, dv, None, None, None, None, None
         with torch.cuda.device(q.device):
             check(
                 lib.vb200_attn_varlen_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(),

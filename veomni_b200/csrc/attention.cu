@@ -586,3 +586,20 @@ extern "C" int vb200_attn_varlen_bwd(const void* q, const void* k, const void* v
     return bwd_impl<64>(q, k, v, o, dout, lse, delta, dq, dk, dv, cu_seqlens, num_seqs, max_seqlen, total, q_heads,
                         k_heads, strides, scale, causal, (cudaStream_t)stream);
 }
+
+// delta[h, t] = sum_d dO[t,h,d] * O[t,h,d]  (the softmax-backward row term; shared by both backward paths)
+extern "C" int vb200_attn_bwd_delta(const void* o, const void* dout, float* delta, int32_t total, int32_t q_heads,
+                                    int32_t head_dim, int64_t o_st, int64_t o_sh, int64_t do_st, int64_t do_sh, void* stream) {
+    if (head_dim != 64 && head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_bwd_delta: head_dim must be 64 or 128");
+    if (total <= 0) return VB200_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (head_dim == 128)
+        attn_bwd_delta_kernel<128><<<vb::kNumSMs * 4, 256, 0, s>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dout, delta,
+                                                                  total, q_heads, o_st, o_sh, do_st, do_sh);
+    else
+        attn_bwd_delta_kernel<64><<<vb::kNumSMs * 4, 256, 0, s>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dout, delta,
+                                                                 total, q_heads, o_st, o_sh, do_st, do_sh);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}

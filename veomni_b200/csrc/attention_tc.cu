@@ -266,6 +266,432 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 }
 
+
+// ================================================================================================
+// backward on tcgen05: dQ kernel (Q-row tiles, streams K/V) and dK/dV kernel (KV-row tiles, streams
+// Q/dO of every q head of the GQA group).  No atomics: same deterministic split as attention.cu.
+//   dQ   : S = Q K^T, dP = dO V^T (TMEM, N=64) -> dS = P o (dP - delta) (softmax warps, bf16 -> smem)
+//          dQ += dS K   (TMEM accumulator for the whole KV sweep, read once at the end)
+//   dKdV : S^T = K Q^T, dP^T = V dO^T (TMEM, N=64) -> P^T, dS^T (bf16 -> smem)
+//          dV += P^T dO, dK += dS^T Q   (TMEM accumulators for the whole sweep)
+// ================================================================================================
+struct AttnTcBwdParams {
+    const int* cu_seqlens;
+    int Hq, Hk, total;
+    float scale;
+    int causal;
+    const float* lse;    // [Hq, total]
+    const float* delta;  // [Hq, total]
+    __nv_bfloat16 *dq, *dk, *dv;
+    int64_t dq_st, dq_sh, dk_st, dk_sh, dv_st, dv_sh;
+};
+
+constexpr int TB_N = 64;                      // streamed tile rows
+constexpr int TB_SMALL = TB_N * TC_D * 2;     // 16 KB: a [64][128] bf16 tile (two 8 KB boxes)
+constexpr int TB_DS = 128 * TB_N * 2;         // 16 KB: a [128][64] bf16 tile (one box)
+
+enum { Q_LOAD = 0, Q_KFULL = 1, Q_VFULL = 3, Q_KEMPTY = 5, Q_VEMPTY = 7, Q_SPFULL = 9, Q_SEMPTY = 11, Q_DSFULL = 13,
+       Q_DSEMPTY = 15, Q_DONE = 17, Q_COUNT = 18 };
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      const AttnTcBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;                    // 32 KB
+    uint8_t* sdO = sQ + TC_TILE;           // 32 KB
+    uint8_t* sK = sdO + TC_TILE;           // 2 x 16 KB
+    uint8_t* sV = sK + 2 * TB_SMALL;       // 2 x 16 KB
+    uint8_t* sdS = sV + 2 * TB_SMALL;      // 2 x 16 KB
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sdS + 2 * TB_DS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + Q_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seq = blockIdx.z, h = blockIdx.y;
+    const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
+    const int mblk = (int)gridDim.x - 1 - (int)blockIdx.x;
+    const int m0 = mblk * TC_BM;
+    if (m0 >= L) return;
+    const int hk = h / (p.Hq / p.Hk);
+    const int kv_end = p.causal ? min(L, m0 + TC_BM) : L;
+    const int n_tiles = (kv_end + TB_N - 1) / TB_N;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Q_COUNT; ++i) {
+            const bool by_warps = (i >= Q_SEMPTY && i < Q_SEMPTY + 2) || (i >= Q_DSFULL && i < Q_DSFULL + 2);
+            mbar_init(&bar[i], by_warps ? 4 : 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // TMEM columns: S[2] 0/64, dP[2] 128/192, dQ 256..383
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(&bar[Q_LOAD], 2 * TC_TILE);
+            for (int hf = 0; hf < 2; ++hf) {
+                tma_load_3d(sQ + hf * TC_BM * 128, &tmQ, hf * 64, h, s0 + m0, &bar[Q_LOAD]);
+                tma_load_3d(sdO + hf * TC_BM * 128, &tmdO, hf * 64, h, s0 + m0, &bar[Q_LOAD]);
+            }
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(&bar[Q_KEMPTY + st], ph ^ 1);
+                mbar_expect_tx(&bar[Q_KFULL + st], TB_SMALL);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_3d(sK + st * TB_SMALL + hf * TB_N * 128, &tmK, hf * 64, hk, s0 + j * TB_N, &bar[Q_KFULL + st]);
+                mbar_wait(&bar[Q_VEMPTY + st], ph ^ 1);
+                mbar_expect_tx(&bar[Q_VFULL + st], TB_SMALL);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_3d(sV + st * TB_SMALL + hf * TB_N * 128, &tmV, hf * 64, hk, s0 + j * TB_N, &bar[Q_VFULL + st]);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_nt = umma_idesc(0, 0, TC_BM, TB_N);   // S, dP: N = 64
+        constexpr uint32_t idesc_dq = umma_idesc(0, 1, TC_BM, TC_D);   // dQ: A = dS (K-major), B = K (MN-major)
+        const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sdO);
+        mbar_wait(&bar[Q_LOAD], 0);
+        for (int j = 0; j <= n_tiles; ++j) {
+            if (j < n_tiles) {
+                const int st = j & 1;
+                const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                mbar_wait(&bar[Q_SEMPTY + st], ph ^ 1);
+                mbar_wait(&bar[Q_KFULL + st], ph);
+                mbar_wait(&bar[Q_VFULL + st], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t k_addr = smem_u32(sK + st * TB_SMALL), v_addr = smem_u32(sV + st * TB_SMALL);
+#pragma unroll
+                    for (int k = 0; k < TC_D / 16; ++k) {
+                        const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
+                        const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16(tmem + st * TB_N, umma_desc(q_addr + a_off, 16, 1024), umma_desc(k_addr + b_off, 16, 1024),
+                                 idesc_nt, k ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < TC_D / 16; ++k) {
+                        const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
+                        const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16(tmem + 128 + st * TB_N, umma_desc(do_addr + a_off, 16, 1024), umma_desc(v_addr + b_off, 16, 1024),
+                                 idesc_nt, k ? 1u : 0u);
+                    }
+                    umma_commit(&bar[Q_VEMPTY + st]);
+                    umma_commit(&bar[Q_SPFULL + st]);
+                }
+                __syncwarp();
+            }
+            if (j >= 1) {
+                const int i = j - 1, st = i & 1;
+                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                mbar_wait(&bar[Q_DSFULL + st], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t ds_addr = smem_u32(sdS + st * TB_DS), k_addr = smem_u32(sK + st * TB_SMALL);
+#pragma unroll
+                    for (int k = 0; k < TB_N / 16; ++k)
+                        umma_f16(tmem + 256, umma_desc(ds_addr + k * 32, 16, 1024),
+                                 umma_desc(k_addr + k * 16 * 128, TB_N * 128, 1024), idesc_dq, (i | k) ? 1u : 0u);
+                    umma_commit(&bar[Q_KEMPTY + st]);
+                    umma_commit(&bar[Q_DSEMPTY + st]);
+                    if (i == n_tiles - 1) umma_commit(&bar[Q_DONE]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int m = m0 + r;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        const float sl2 = p.scale * kLog2eTc;
+        float lse2 = 0.f, dl = 0.f;
+        if (m < L) {
+            const float l = p.lse[(int64_t)h * p.total + s0 + m];
+            lse2 = (l == -INFINITY) ? 0.f : l * kLog2eTc;
+            dl = p.delta[(int64_t)h * p.total + s0 + m];
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j & 1;
+            const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+            mbar_wait(&bar[Q_SPFULL + st], ph);
+            tc_fence_after();
+            mbar_wait(&bar[Q_DSEMPTY + st], ph ^ 1);  // dS[st] free (dQ_{j-2} committed)
+            const uint32_t ds_a = smem_u32(sdS + st * TB_DS);
+#pragma unroll 1
+            for (int c = 0; c < TB_N / 32; ++c) {
+                uint32_t sv[32], dv[32];
+                tmem_ld32(lane_base + st * TB_N + c * 32, sv);
+                tmem_ld32(lane_base + 128 + st * TB_N + c * 32, dv);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float d0, d1;
+                    {
+                        const int n = j * TB_N + c * 32 + i;
+                        const bool ok0 = n < L && m < L && (!p.causal || n <= m);
+                        const bool ok1 = n + 1 < L && m < L && (!p.causal || n + 1 <= m);
+                        const float p0 = ok0 ? exp2f(__uint_as_float(sv[i]) * sl2 - lse2) : 0.f;
+                        const float p1 = ok1 ? exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse2) : 0.f;
+                        d0 = p0 * (__uint_as_float(dv[i]) - dl);
+                        d1 = p1 * (__uint_as_float(dv[i + 1]) - dl);
+                    }
+                    pk[i >> 1] = f2_to_bf2(d0, d1);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t addr = swz_addr(ds_a, TC_BM, r, c * 4 + g);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                                 "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
+                }
+            }
+            tc_fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bar[Q_SEMPTY + st]);
+                mbar_arrive(&bar[Q_DSFULL + st]);
+            }
+        }
+        mbar_wait(&bar[Q_DONE], 0);
+        tc_fence_after();
+        __nv_bfloat16* row = p.dq + (int64_t)(s0 + m) * p.dq_st + (int64_t)h * p.dq_sh;
+#pragma unroll 1
+        for (int c = 0; c < TC_D / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + 256 + c * 32, v);
+            if (m < L) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 w;
+                    w.x = f2_to_bf2(__uint_as_float(v[g * 8 + 0]) * p.scale, __uint_as_float(v[g * 8 + 1]) * p.scale);
+                    w.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * p.scale, __uint_as_float(v[g * 8 + 3]) * p.scale);
+                    w.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * p.scale, __uint_as_float(v[g * 8 + 5]) * p.scale);
+                    w.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * p.scale, __uint_as_float(v[g * 8 + 7]) * p.scale);
+                    *reinterpret_cast<uint4*>(row + c * 32 + g * 8) = w;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = 3, K_STFULL = 5, K_STEMPTY = 7, K_PFULL = 9, K_PEMPTY = 11, K_DONE = 13,
+       K_COUNT = 14 };
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                        const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                        const AttnTcBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sK = smem;                    // 32 KB
+    uint8_t* sV = sK + TC_TILE;            // 32 KB
+    uint8_t* sQ = sV + TC_TILE;            // 2 x 16 KB
+    uint8_t* sdO = sQ + 2 * TB_SMALL;      // 2 x 16 KB
+    uint8_t* sPt = sdO + 2 * TB_SMALL;     // 2 x 16 KB
+    uint8_t* sdSt = sPt + 2 * TB_DS;       // 2 x 16 KB
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sdSt + 2 * TB_DS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + K_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seq = blockIdx.z, hk = blockIdx.y;
+    const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
+    const int n0 = blockIdx.x * TC_BM;
+    if (n0 >= L) return;
+    const int G = p.Hq / p.Hk;
+    const int i_start = p.causal ? n0 / TB_N : 0;
+    const int nq = (L + TB_N - 1) / TB_N - i_start;
+    const int jobs = nq * G;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < K_COUNT; ++i) {
+            const bool by_warps = (i >= K_STEMPTY && i < K_STEMPTY + 2) || (i >= K_PFULL && i < K_PFULL + 2);
+            mbar_init(&bar[i], by_warps ? 4 : 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // TMEM columns: S^T[2] 0/64, dP^T[2] 128/192, dV 256..383, dK 384..511
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(&bar[K_LOAD], 2 * TC_TILE);
+            for (int hf = 0; hf < 2; ++hf) {
+                tma_load_3d(sK + hf * TC_BM * 128, &tmK, hf * 64, hk, s0 + n0, &bar[K_LOAD]);
+                tma_load_3d(sV + hf * TC_BM * 128, &tmV, hf * 64, hk, s0 + n0, &bar[K_LOAD]);
+            }
+            for (int jb = 0; jb < jobs; ++jb) {
+                const int st = jb & 1;
+                const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
+                const int hh = hk * G + jb / nq, qi = i_start + jb % nq;
+                mbar_wait(&bar[K_QEMPTY + st], ph ^ 1);
+                mbar_expect_tx(&bar[K_QFULL + st], 2 * TB_SMALL);
+                for (int hf = 0; hf < 2; ++hf) {
+                    tma_load_3d(sQ + st * TB_SMALL + hf * TB_N * 128, &tmQ, hf * 64, hh, s0 + qi * TB_N, &bar[K_QFULL + st]);
+                    tma_load_3d(sdO + st * TB_SMALL + hf * TB_N * 128, &tmdO, hf * 64, hh, s0 + qi * TB_N, &bar[K_QFULL + st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_nt = umma_idesc(0, 0, TC_BM, TB_N);
+        constexpr uint32_t idesc_acc = umma_idesc(0, 1, TC_BM, TC_D);
+        const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+        mbar_wait(&bar[K_LOAD], 0);
+        for (int jb = 0; jb <= jobs; ++jb) {
+            if (jb < jobs) {
+                const int st = jb & 1;
+                const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
+                mbar_wait(&bar[K_STEMPTY + st], ph ^ 1);
+                mbar_wait(&bar[K_QFULL + st], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t q_addr = smem_u32(sQ + st * TB_SMALL), do_addr = smem_u32(sdO + st * TB_SMALL);
+#pragma unroll
+                    for (int k = 0; k < TC_D / 16; ++k) {
+                        const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
+                        const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16(tmem + st * TB_N, umma_desc(k_addr + a_off, 16, 1024), umma_desc(q_addr + b_off, 16, 1024),
+                                 idesc_nt, k ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < TC_D / 16; ++k) {
+                        const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
+                        const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16(tmem + 128 + st * TB_N, umma_desc(v_addr + a_off, 16, 1024), umma_desc(do_addr + b_off, 16, 1024),
+                                 idesc_nt, k ? 1u : 0u);
+                    }
+                    umma_commit(&bar[K_STFULL + st]);
+                }
+                __syncwarp();
+            }
+            if (jb >= 1) {
+                const int i = jb - 1, st = i & 1;
+                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                mbar_wait(&bar[K_PFULL + st], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t pt_addr = smem_u32(sPt + st * TB_DS), dst_addr = smem_u32(sdSt + st * TB_DS);
+                    const uint32_t q_addr = smem_u32(sQ + st * TB_SMALL), do_addr = smem_u32(sdO + st * TB_SMALL);
+#pragma unroll
+                    for (int k = 0; k < TB_N / 16; ++k)
+                        umma_f16(tmem + 256, umma_desc(pt_addr + k * 32, 16, 1024),
+                                 umma_desc(do_addr + k * 16 * 128, TB_N * 128, 1024), idesc_acc, (i | k) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < TB_N / 16; ++k)
+                        umma_f16(tmem + 384, umma_desc(dst_addr + k * 32, 16, 1024),
+                                 umma_desc(q_addr + k * 16 * 128, TB_N * 128, 1024), idesc_acc, (i | k) ? 1u : 0u);
+                    umma_commit(&bar[K_QEMPTY + st]);
+                    umma_commit(&bar[K_PEMPTY + st]);
+                    if (i == jobs - 1) umma_commit(&bar[K_DONE]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int n = n0 + r;  // kv index of this thread's row
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        const float sl2 = p.scale * kLog2eTc;
+        for (int jb = 0; jb < jobs; ++jb) {
+            const int st = jb & 1;
+            const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
+            const int hh = hk * G + jb / nq, qi = i_start + jb % nq;
+            const float* lse_row = p.lse + (int64_t)hh * p.total + s0;
+            const float* dl_row = p.delta + (int64_t)hh * p.total + s0;
+            mbar_wait(&bar[K_STFULL + st], ph);
+            tc_fence_after();
+            mbar_wait(&bar[K_PEMPTY + st], ph ^ 1);
+            const uint32_t pt_a = smem_u32(sPt + st * TB_DS), dst_a = smem_u32(sdSt + st * TB_DS);
+#pragma unroll 1
+            for (int c = 0; c < TB_N / 32; ++c) {
+                uint32_t sv[32], dv[32];
+                tmem_ld32(lane_base + st * TB_N + c * 32, sv);
+                tmem_ld32(lane_base + 128 + st * TB_N + c * 32, dv);
+                uint32_t pk[16], dk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float pe[2], de[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int m = qi * TB_N + c * 32 + i + e;  // q index (column)
+                        const bool ok = n < L && m < L && (!p.causal || n <= m);
+                        float l2 = 0.f, dlt = 0.f;
+                        if (m < L) {
+                            const float l = __ldg(lse_row + m);
+                            l2 = (l == -INFINITY) ? 0.f : l * kLog2eTc;
+                            dlt = __ldg(dl_row + m);
+                        }
+                        pe[e] = ok ? exp2f(__uint_as_float(sv[i + e]) * sl2 - l2) : 0.f;
+                        de[e] = pe[e] * (__uint_as_float(dv[i + e]) - dlt);
+                    }
+                    pk[i >> 1] = f2_to_bf2(pe[0], pe[1]);
+                    dk[i >> 1] = f2_to_bf2(de[0], de[1]);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t a1 = swz_addr(pt_a, TC_BM, r, c * 4 + g), a2 = swz_addr(dst_a, TC_BM, r, c * 4 + g);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                                 "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a2), "r"(dk[g * 4]), "r"(dk[g * 4 + 1]),
+                                 "r"(dk[g * 4 + 2]), "r"(dk[g * 4 + 3]) : "memory");
+                }
+            }
+            tc_fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bar[K_STEMPTY + st]);
+                mbar_arrive(&bar[K_PFULL + st]);
+            }
+        }
+        mbar_wait(&bar[K_DONE], 0);
+        tc_fence_after();
+        __nv_bfloat16* vrow = p.dv + (int64_t)(s0 + n) * p.dv_st + (int64_t)hk * p.dv_sh;
+        __nv_bfloat16* krow = p.dk + (int64_t)(s0 + n) * p.dk_st + (int64_t)hk * p.dk_sh;
+#pragma unroll 1
+        for (int c = 0; c < TC_D / 32; ++c) {
+            uint32_t v[32], kk[32];
+            tmem_ld32(lane_base + 256 + c * 32, v);
+            tmem_ld32(lane_base + 384 + c * 32, kk);
+            if (n < L) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 w, x;
+                    w.x = f2_to_bf2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+                    w.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+                    w.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+                    w.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+                    x.x = f2_to_bf2(__uint_as_float(kk[g * 8 + 0]) * p.scale, __uint_as_float(kk[g * 8 + 1]) * p.scale);
+                    x.y = f2_to_bf2(__uint_as_float(kk[g * 8 + 2]) * p.scale, __uint_as_float(kk[g * 8 + 3]) * p.scale);
+                    x.z = f2_to_bf2(__uint_as_float(kk[g * 8 + 4]) * p.scale, __uint_as_float(kk[g * 8 + 5]) * p.scale);
+                    x.w = f2_to_bf2(__uint_as_float(kk[g * 8 + 6]) * p.scale, __uint_as_float(kk[g * 8 + 7]) * p.scale);
+                    *reinterpret_cast<uint4*>(vrow + c * 32 + g * 8) = w;
+                    *reinterpret_cast<uint4*>(krow + c * 32 + g * 8) = x;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -296,6 +722,54 @@ extern "C" int vb200_attn_varlen_fwd_tc(const void* q, const void* k, const void
     dim3 grid((max_seqlen + TC_BM - 1) / TC_BM, q_heads, num_seqs);
     attn_fwd_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+// dq/dk/dv through the tcgen05 kernels; `delta` must already hold rowsum(dO*O) (vb200_attn_varlen_bwd computes it
+// the same way: call vb200_attn_bwd_delta first).
+extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                                        const float* delta, void* dq, void* dk, void* dv, const int32_t* cu_seqlens,
+                                        int32_t num_seqs, int32_t max_seqlen, int32_t total, int32_t q_heads,
+                                        int32_t k_heads, int32_t head_dim, const int64_t* st, float scale, int32_t causal,
+                                        void* stream) {
+    // st: (tok, head) strides of q, k, v, dout, dq, dk, dv
+    if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: head_dim must be 128");
+    if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: Hq % Hk != 0");
+    for (int i = 0; i < 14; ++i)
+        if (st[i] & 7) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: strides must be multiples of 8 elements");
+    if (total <= 0 || num_seqs <= 0 || max_seqlen <= 0) return VB200_OK;
+    CUtensorMap tmQ128, tmdO128, tmK64, tmV64, tmK128, tmV128, tmQ64, tmdO64;
+    int rc;
+    if ((rc = make_tmap_3d(&tmQ128, q, 128, q_heads, total, st[1], st[0], 128))) return rc;
+    if ((rc = make_tmap_3d(&tmdO128, dout, 128, q_heads, total, st[7], st[6], 128))) return rc;
+    if ((rc = make_tmap_3d(&tmK64, k, 128, k_heads, total, st[3], st[2], 64))) return rc;
+    if ((rc = make_tmap_3d(&tmV64, v, 128, k_heads, total, st[5], st[4], 64))) return rc;
+    if ((rc = make_tmap_3d(&tmK128, k, 128, k_heads, total, st[3], st[2], 128))) return rc;
+    if ((rc = make_tmap_3d(&tmV128, v, 128, k_heads, total, st[5], st[4], 128))) return rc;
+    if ((rc = make_tmap_3d(&tmQ64, q, 128, q_heads, total, st[1], st[0], 64))) return rc;
+    if ((rc = make_tmap_3d(&tmdO64, dout, 128, q_heads, total, st[7], st[6], 64))) return rc;
+    AttnTcBwdParams p{};
+    p.cu_seqlens = cu_seqlens; p.Hq = q_heads; p.Hk = k_heads; p.total = total; p.scale = scale; p.causal = causal;
+    p.lse = lse; p.delta = delta;
+    p.dq = (__nv_bfloat16*)dq; p.dq_st = st[8]; p.dq_sh = st[9];
+    p.dk = (__nv_bfloat16*)dk; p.dk_st = st[10]; p.dk_sh = st[11];
+    p.dv = (__nv_bfloat16*)dv; p.dv_st = st[12]; p.dv_sh = st[13];
+    const size_t smem_dq = 2 * TC_TILE + 4 * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
+    const size_t smem_kv = 2 * TC_TILE + 4 * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 64;
+    static bool attr = false;
+    if (!attr) {
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+        attr = true;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 gq((max_seqlen + TC_BM - 1) / TC_BM, q_heads, num_seqs);
+    attn_bwd_dq_tc_kernel<<<gq, 192, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+    VB_HOST_CHECK_LAUNCH();
+    dim3 gk((max_seqlen + TC_BM - 1) / TC_BM, k_heads, num_seqs);
+    attn_bwd_dkdv_tc_kernel<<<gk, 192, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+    vb200_count_launch(2);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
 }
