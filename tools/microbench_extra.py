@@ -60,3 +60,53 @@ def bench_attention(dev, iters):
 
 
 BENCHES = {"attention": bench_attention}
+
+
+def bench_moe(dev, iters):
+    """Qwen3-30B-A3B layer shapes: T=4096 tokens, top-8 of 128 experts, H=2048, I=768 (T*K = 32768 rows)."""
+    from veomni_b200.moe import fused_moe_forward, group_gemm_same_mn, group_gemm_same_nk, moe_gather, moe_route, moe_scatter
+
+    T, E, K, H, I = 4096, 128, 8, 2048, 768
+    g = torch.Generator(device=dev).manual_seed(0)
+    logits = torch.randn(T, E, device=dev, generator=g)
+    rw, idx = torch.topk(torch.softmax(logits, -1), K, dim=-1)
+    rw = (rw / rw.sum(-1, keepdim=True)).to(BF)
+    hs = (0.1 * torch.randn(T, H, device=dev, generator=g)).to(BF)
+    w1 = (0.1 * torch.randn(E, 2 * I, H, device=dev, generator=g)).to(BF)
+    w2 = (0.1 * torch.randn(E, H, I, device=dev, generator=g)).to(BF)
+    with torch.no_grad():
+        report("moe_route[32768 slots,128e]", time_fn(lambda: moe_route(idx, E), [()], iters))
+        splits, cumsum, sidx = moe_route(idx, E)
+        report("moe_scatter[4096x8x2048]", time_fn(lambda: moe_scatter(hs, sidx), [()], iters), nbytes=(T + T * K) * H * 2)
+        x = moe_scatter(hs, sidx)
+        report("moe_gather[4096x8x2048]", time_fn(lambda: moe_gather(x, sidx), [()], iters), nbytes=(T + T * K) * H * 2)
+        report("group_gemm_NT fc1[32768x2048 -> 1536]", time_fn(lambda: group_gemm_same_nk(x, w1, cumsum, transpose_b=True), [()], iters),
+               flops=2 * T * K * 2 * I * H)
+        a = group_gemm_same_nk(x, w1, cumsum, transpose_b=True)
+        act = a[:, :I].contiguous()
+        report("group_gemm_NT fc2[32768x768 -> 2048]", time_fn(lambda: group_gemm_same_nk(act, w2, cumsum, transpose_b=True), [()], iters),
+               flops=2 * T * K * I * H)
+        report("group_gemm_NN dgrad fc1[32768x1536 -> 2048]", time_fn(lambda: group_gemm_same_nk(a, w1, cumsum, transpose_b=False), [()], iters),
+               flops=2 * T * K * 2 * I * H)
+        gw = torch.empty_like(w1)
+        report("group_gemm_TN wgrad fc1[128 x 1536x2048, K=32768]", time_fn(lambda: group_gemm_same_mn(a, x, gw, cumsum), [()], iters),
+               flops=2 * T * K * 2 * I * H)
+    hs_g, w1_g, w2_g, rw_g = (t.clone().requires_grad_(True) for t in (hs, w1, w2, rw))
+
+    def fb():
+        out = fused_moe_forward(E, rw_g, idx, hs_g, None, None, w2_g, fc1_1_2_weight=w1_g)
+        out.backward(hs)
+        hs_g.grad = w1_g.grad = w2_g.grad = rw_g.grad = None
+
+    report("fused_moe fwd+bwd[Qwen3-30B-A3B layer, T=4096]", time_fn(fb, [()], iters), flops=3 * 2 * T * K * 3 * I * H)
+    try:  # library reference: cuBLAS dense GEMM of the same FLOPs
+        a2 = torch.randn(T * K, H, device=dev, dtype=BF)
+        b2 = torch.randn(2 * I, H, device=dev, dtype=BF)
+        with torch.no_grad():
+            report("(lib) cublas dense [32768x2048]x[2048x1536]", time_fn(lambda: torch.nn.functional.linear(a2, b2), [()], iters),
+                   flops=2 * T * K * 2 * I * H)
+    except Exception as ex:  # noqa: BLE001
+        print({"cublas": str(ex)})
+
+
+BENCHES["moe"] = bench_moe
