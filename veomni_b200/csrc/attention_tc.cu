@@ -5,12 +5,12 @@
 //
 //   warp 0      TMA producer   Q once; K_j / V_j tiles (128 kv rows) into 2-stage smem rings (SWIZZLE_128B boxes)
 //   warp 1      MMA issuer     S_j  = Q K_j^T   tcgen05.mma M128 N128 K16 x8, K-major A/B      -> TMEM S[j&1]
-//                              OT_j = P_j V_j   tcgen05.mma, A = P (smem, K-major), B = V (MN-major) -> TMEM OT[j&1]
+//                              O   += P_j V_j   tcgen05.mma, A = P (smem, K-major), B = V (MN-major) -> TMEM O
 //                              (S_{j+1} is issued before PV_j so the tensor pipe runs ahead of the softmax)
-//   warps 2..5  softmax        thread == query row (TMEM lane): pass 1 row max from tcgen05.ld, pass 2 exp2 -> bf16 P
-//                              written to swizzled smem; O accumulates in registers: O = alpha*O + OT (no TMEM
-//                              read-modify-write correction pass); LSE saved for the backward
-// TMEM: 512 columns = S[2] (2x128) + OT[2] (2x128).  smem: Q 32 KB + K 2x32 KB + V 2x32 KB + P 32 KB.
+//   warps 2..5  softmax        thread == query row (TMEM lane): S read once by tcgen05.ld, row max, exp2 -> bf16 P written
+//                              to swizzled smem; O stays in TMEM (PV accumulates into it) and is only rescaled when a
+//                              row max grows by more than 2^8 (lazy rescale); LSE saved for the backward
+// TMEM: S[2] (2x128 columns) + O (128 columns).  smem: Q 32 KB + K 2x32 KB + V 2x32 KB + P 32 KB.
 // All hand-offs are mbarriers (TMA tx-count, tcgen05.commit, thread arrives) — no __syncthreads in the loop.
 #include "umma.cuh"
 
@@ -30,11 +30,33 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_D = 128;
 constexpr int TC_TILE = TC_BM * TC_D * 2;  // 32 KB
 constexpr float kLog2eTc = 1.4426950408889634f;
 
+// Row max of a 128-column S tile held in registers; MASK applies the causal / sequence-end mask in place.
+template <bool MASK>
+__device__ __forceinline__ float tile_row_max(uint32_t (&sv)[4][32], int n0, int m, int L, int causal) {
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (MASK) {
+                const int n = n0 + c * 32 + i;
+                if (n >= L || (causal && n > m)) sv[c][i] = 0xff800000u;  // -inf
+            }
+            mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[c][i]));
+        }
+    }
+    return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+}
+
 enum {  // barrier indices
     B_Q = 0, B_KFULL = 1, B_VFULL = 3, B_KEMPTY = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11, B_PFULL = 13,
-    B_PEMPTY = 14, B_OFULL = 15, B_OEMPTY = 17, B_COUNT = 19
+    B_PVDONE = 14, B_COUNT = 15
 };
 
+// Forward v2 (FA4-style data flow): O stays resident in TMEM for the whole KV sweep (the PV MMAs accumulate
+// into it), S is read from TMEM exactly once per tile, and the running max used in the exponentials is only
+// refreshed — with a TMEM read-modify-write of O — when a row's new max exceeds it by more than 2^8
+// ("lazy rescale"); TMEM read bandwidth, not the tensor pipe, is the scarce resource in this kernel.
 __global__ void __launch_bounds__(192, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -58,7 +80,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < B_COUNT; ++i) {
-            const bool by_warps = (i >= B_SEMPTY && i < B_SEMPTY + 2) || i == B_PFULL || (i >= B_OEMPTY && i < B_OEMPTY + 2);
+            const bool by_warps = (i >= B_SEMPTY && i < B_SEMPTY + 2) || i == B_PFULL;
             mbar_init(&bar[i], by_warps ? 4 : 1);
         }
         mbar_fence_init();
@@ -69,6 +91,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // TMEM columns: S[2] 0/128, O 256..383
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -115,10 +138,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
                 __syncwarp();
             }
-            if (j >= 1) {  // OT_{j-1} = P_{j-1} V_{j-1}
+            if (j >= 1) {  // O += P_{j-1} V_{j-1}
                 const int i = j - 1, st = i & 1;
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                mbar_wait(&bar[B_OEMPTY + st], ph ^ 1);
                 mbar_wait(&bar[B_VFULL + st], ph);
                 mbar_wait(&bar[B_PFULL], (uint32_t)i & 1u);
                 tc_fence_after();
@@ -127,136 +149,112 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < TC_BN / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16(tmem + 256 + st * TC_D, umma_desc(p_addr + a_off, 16, 1024),
-                                 umma_desc(v_addr + k * 16 * 128, TC_BN * 128, 1024), idesc_pv, k ? 1u : 0u);
+                        umma_f16(tmem + 256, umma_desc(p_addr + a_off, 16, 1024),
+                                 umma_desc(v_addr + k * 16 * 128, TC_BN * 128, 1024), idesc_pv, (i | k) ? 1u : 0u);
                     }
                     umma_commit(&bar[B_VEMPTY + st]);
-                    umma_commit(&bar[B_PEMPTY]);
-                    umma_commit(&bar[B_OFULL + st]);
+                    umma_commit(&bar[B_PVDONE]);
                 }
                 __syncwarp();
             }
         }
     } else {
-        // ===== softmax + output accumulation: thread == query row =====
+        // ===== softmax: thread == query row =====
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int m = m0 + r;  // sequence-relative query index
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         const float sl2 = p.scale * kLog2eTc;
-        float o_acc[TC_D];
-#pragma unroll
-        for (int i = 0; i < TC_D; ++i) o_acc[i] = 0.f;
-        float m_i = -INFINITY, l_i = 0.f, alpha_lag = 1.f;
+        float m_ref = 0.f, l_i = 0.f;  // m_ref: the (possibly stale) max the exponentials are taken against
         const uint32_t sP_a = smem_u32(sP);
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j & 1;
             const uint32_t ph = (uint32_t)(j >> 1) & 1u;
             mbar_wait(&bar[B_SFULL + st], ph);
             tc_fence_after();
-            const bool need_mask = (j * TC_BN + TC_BN > L) || (p.causal && j * TC_BN + TC_BN > m0);
-            // pass 1: row max
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + st * TC_BN + c * 32, v);
+            uint32_t sv[4][32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float s = __uint_as_float(v[i]);
-                    if (need_mask) {
-                        const int n = j * TC_BN + c * 32 + i;
-                        if (n >= L || (p.causal && n > m)) s = -INFINITY;
-                    }
-                    mx = fmaxf(mx, s);
-                }
+            for (int c = 0; c < 4; ++c) tmem_ld32_nowait(lane_base + st * TC_BN + c * 32, sv[c]);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[B_SEMPTY + st]);  // S[st] is in registers: the next QK^T may overwrite it
+
+            const bool need_mask = (j * TC_BN + TC_BN > L) || (p.causal && j * TC_BN + TC_BN > m0);
+            const float mx = need_mask ? tile_row_max<true>(sv, j * TC_BN, m, L, p.causal)
+                                       : tile_row_max<false>(sv, j * TC_BN, m, L, p.causal);
+            // lazy rescale: refresh m_ref only when this tile exceeds it by more than 2^8 (or on the first tile)
+            float alpha = 1.f;
+            bool refresh = false;
+            if (j == 0) {
+                m_ref = (mx == -INFINITY) ? 0.f : mx;
+            } else if (mx != -INFINITY && (mx - m_ref) * sl2 > 8.0f) {
+                alpha = exp2f((m_ref - mx) * sl2);
+                m_ref = mx;
+                refresh = true;
             }
-            const float m_new = fmaxf(m_i, mx);
-            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-            const float alpha = exp2f((m_i - m_use) * sl2);
-            m_i = m_new;
-            // the P buffer is free once PV_{j-1} has been committed
-            if (j >= 1) mbar_wait(&bar[B_PEMPTY], (uint32_t)(j - 1) & 1u);
-            // pass 2: P = exp2(S*sl2 - m*sl2) -> bf16, swizzled K-major smem tile; row sum
-            float sum = 0.f;
-            const float mb = m_use * sl2;
+            // P buffer free <=> PV_{j-1} committed; the same barrier also means O holds tiles 0..j-1
+            if (j >= 1) mbar_wait(&bar[B_PVDONE], (uint32_t)(j - 1) & 1u);
+            if (__any_sync(0xffffffffu, refresh)) {  // warp-collective TMEM read-modify-write of O
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + st * TC_BN + c * 32, v);
+                for (int c = 0; c < TC_D / 32; ++c) {
+                    uint32_t ov[32];
+                    tmem_ld32(lane_base + 256 + c * 32, ov);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                    tmem_st32(lane_base + 256 + c * 32, ov);
+                }
+                tmem_wait_st();
+                l_i *= alpha;
+            }
+            const float mb = m_ref * sl2;
+            float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float e0 = exp2f(__uint_as_float(v[i]) * sl2 - mb), e1 = exp2f(__uint_as_float(v[i + 1]) * sl2 - mb);
-                    if (need_mask) {
-                        const int n = j * TC_BN + c * 32 + i;
-                        if (n >= L || (p.causal && n > m)) e0 = 0.f;
-                        if (n + 1 >= L || (p.causal && n + 1 > m)) e1 = 0.f;
-                    }
-                    sum += e0 + e1;
+                    const float e0 = exp2f(__uint_as_float(sv[c][i]) * sl2 - mb);      // -inf -> 0
+                    const float e1 = exp2f(__uint_as_float(sv[c][i + 1]) * sl2 - mb);
+                    sum4[(i >> 1) & 3] += e0 + e1;
                     pk[i >> 1] = f2_to_bf2(e0, e1);
                 }
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {  // 4 x 16-byte chunks = 32 columns
-                    const int chunk = c * 4 + g;  // 0..15 over the 128 kv columns
-                    const uint32_t addr = swz_addr(sP_a, TC_BM, r, chunk);
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t addr = swz_addr(sP_a, TC_BM, r, c * 4 + g);
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
                                  "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
                 }
             }
-            l_i = l_i * alpha + sum;
+            l_i += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
             tc_fence_before();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bar[B_SEMPTY + st]);
-                mbar_arrive(&bar[B_PFULL]);
-            }
-            // fold in OT_{j-1}
-            if (j >= 1) {
-                const int ost = (j - 1) & 1;
-                mbar_wait(&bar[B_OFULL + ost], (uint32_t)((j - 1) >> 1) & 1u);
-                tc_fence_after();
+            if (lane == 0) mbar_arrive(&bar[B_PFULL]);
+        }
+        mbar_wait(&bar[B_PVDONE], (uint32_t)(n_tiles - 1) & 1u);
+        tc_fence_after();
+        const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
+        if (m < L) p.lse[(int64_t)h * p.total + s0 + m] = (l_i > 0.f) ? m_ref * p.scale + logf(l_i) : -INFINITY;
+        __nv_bfloat16* orow = p.o + (int64_t)(s0 + m) * p.o_stride_tok + (int64_t)h * p.o_stride_head;
+#pragma unroll 1
+        for (int c = 0; c < TC_D / 32; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(lane_base + 256 + c * 32, ov);
+            if (m < L) {
 #pragma unroll
-                for (int c = 0; c < TC_D / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_base + 256 + ost * TC_D + c * 32, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_lag, __uint_as_float(v[i]));
+                for (int g = 0; g < 4; ++g) {
+                    uint4 w;
+                    w.x = f2_to_bf2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+                    w.y = f2_to_bf2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+                    w.z = f2_to_bf2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+                    w.w = f2_to_bf2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = w;
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar[B_OEMPTY + ost]);
-            }
-            alpha_lag = alpha;
-        }
-        {   // last tile's OT
-            const int ost = (n_tiles - 1) & 1;
-            mbar_wait(&bar[B_OFULL + ost], (uint32_t)((n_tiles - 1) >> 1) & 1u);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < TC_D / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + 256 + ost * TC_D + c * 32, v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_lag, __uint_as_float(v[i]));
-            }
-            tc_fence_before();
-        }
-        if (m < L) {
-            const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
-            p.lse[(int64_t)h * p.total + s0 + m] = (l_i > 0.f) ? m_i * p.scale + logf(l_i) : -INFINITY;
-            __nv_bfloat16* orow = p.o + (int64_t)(s0 + m) * p.o_stride_tok + (int64_t)h * p.o_stride_head;
-#pragma unroll
-            for (int c = 0; c < TC_D / 8; ++c) {
-                uint4 w;
-                w.x = f2_to_bf2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
-                w.y = f2_to_bf2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
-                w.z = f2_to_bf2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
-                w.w = f2_to_bf2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
-                *reinterpret_cast<uint4*>(orow + c * 8) = w;
             }
         }
+        tc_fence_before();
     }
     tc_fence_before();
     __syncthreads();
@@ -265,7 +263,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_dealloc(tmem, 512);
     }
 }
-
 
 // ================================================================================================
 // backward on tcgen05: dQ kernel (Q-row tiles, streams K/V) and dK/dV kernel (KV-row tiles, streams
@@ -420,25 +417,32 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             tc_fence_after();
             mbar_wait(&bar[Q_DSEMPTY + st], ph ^ 1);  // dS[st] free (dQ_{j-2} committed)
             const uint32_t ds_a = smem_u32(sdS + st * TB_DS);
+            // tiles fully below the diagonal and inside the sequence need no per-element predicate
+            const bool need_mask = (j * TB_N + TB_N > L) || (m0 + TC_BM > L) || (p.causal && j * TB_N + TB_N > m0);
 #pragma unroll 1
             for (int c = 0; c < TB_N / 32; ++c) {
                 uint32_t sv[32], dv[32];
-                tmem_ld32(lane_base + st * TB_N + c * 32, sv);
-                tmem_ld32(lane_base + 128 + st * TB_N + c * 32, dv);
+                tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
+                tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
+                tmem_wait_ld();
                 uint32_t pk[16];
+                if (need_mask) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float d0, d1;
-                    {
+                    for (int i = 0; i < 32; i += 2) {
                         const int n = j * TB_N + c * 32 + i;
                         const bool ok0 = n < L && m < L && (!p.causal || n <= m);
                         const bool ok1 = n + 1 < L && m < L && (!p.causal || n + 1 <= m);
                         const float p0 = ok0 ? exp2f(__uint_as_float(sv[i]) * sl2 - lse2) : 0.f;
                         const float p1 = ok1 ? exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse2) : 0.f;
-                        d0 = p0 * (__uint_as_float(dv[i]) - dl);
-                        d1 = p1 * (__uint_as_float(dv[i + 1]) - dl);
+                        pk[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(dv[i]) - dl), p1 * (__uint_as_float(dv[i + 1]) - dl));
                     }
-                    pk[i >> 1] = f2_to_bf2(d0, d1);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = exp2f(__uint_as_float(sv[i]) * sl2 - lse2);
+                        const float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse2);
+                        pk[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(dv[i]) - dl), p1 * (__uint_as_float(dv[i + 1]) - dl));
+                    }
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -500,6 +504,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     uint8_t* sdSt = sPt + 2 * TB_DS;       // 2 x 16 KB
     uint64_t* bar = reinterpret_cast<uint64_t*>(sdSt + 2 * TB_DS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + K_COUNT);
+    float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2 stages][lse2 x64 | delta x64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int seq = blockIdx.z, hk = blockIdx.y;
     const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
@@ -608,36 +613,56 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             const int st = jb & 1;
             const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
             const int hh = hk * G + jb / nq, qi = i_start + jb % nq;
-            const float* lse_row = p.lse + (int64_t)hh * p.total + s0;
-            const float* dl_row = p.delta + (int64_t)hh * p.total + s0;
+            // per-column (q index) softmax statistics of this q tile: 64 lse + 64 delta values through smem
+            {
+                float* stat = sStat + st * 128;
+                const int mm = qi * TB_N + (r & 63);
+                float val = 0.f;
+                if (mm < L) {
+                    if (r < 64) {
+                        const float l = p.lse[(int64_t)hh * p.total + s0 + mm];
+                        val = (l == -INFINITY) ? 0.f : l * kLog2eTc;
+                    } else {
+                        val = p.delta[(int64_t)hh * p.total + s0 + mm];
+                    }
+                }
+                stat[r] = val;
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 softmax warps only
+            }
+            const float* lse_s = sStat + st * 128;
+            const float* dl_s = lse_s + 64;
             mbar_wait(&bar[K_STFULL + st], ph);
             tc_fence_after();
             mbar_wait(&bar[K_PEMPTY + st], ph ^ 1);
             const uint32_t pt_a = smem_u32(sPt + st * TB_DS), dst_a = smem_u32(sdSt + st * TB_DS);
+            const bool need_mask = (qi * TB_N + TB_N > L) || (n0 + TC_BM > L) || (p.causal && n0 + TC_BM > qi * TB_N);
 #pragma unroll 1
             for (int c = 0; c < TB_N / 32; ++c) {
                 uint32_t sv[32], dv[32];
-                tmem_ld32(lane_base + st * TB_N + c * 32, sv);
-                tmem_ld32(lane_base + 128 + st * TB_N + c * 32, dv);
+                tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
+                tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
+                tmem_wait_ld();
                 uint32_t pk[16], dk[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float pe[2], de[2];
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c * 32 + i);
+                    const float4 d4 = *reinterpret_cast<const float4*>(dl_s + c * 32 + i);
+                    const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dlv[4] = {d4.x, d4.y, d4.z, d4.w};
+                    float pe[4], de[4];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int m = qi * TB_N + c * 32 + i + e;  // q index (column)
-                        const bool ok = n < L && m < L && (!p.causal || n <= m);
-                        float l2 = 0.f, dlt = 0.f;
-                        if (m < L) {
-                            const float l = __ldg(lse_row + m);
-                            l2 = (l == -INFINITY) ? 0.f : l * kLog2eTc;
-                            dlt = __ldg(dl_row + m);
+                    for (int e = 0; e < 4; ++e) {
+                        float pv = exp2f(__uint_as_float(sv[i + e]) * sl2 - lv[e]);
+                        if (need_mask) {
+                            const int m = qi * TB_N + c * 32 + i + e;  // q index (column)
+                            if (!(n < L && m < L && (!p.causal || n <= m))) pv = 0.f;
                         }
-                        pe[e] = ok ? exp2f(__uint_as_float(sv[i + e]) * sl2 - l2) : 0.f;
-                        de[e] = pe[e] * (__uint_as_float(dv[i + e]) - dlt);
+                        pe[e] = pv;
+                        de[e] = pv * (__uint_as_float(dv[i + e]) - dlv[e]);
                     }
                     pk[i >> 1] = f2_to_bf2(pe[0], pe[1]);
+                    pk[(i >> 1) + 1] = f2_to_bf2(pe[2], pe[3]);
                     dk[i >> 1] = f2_to_bf2(de[0], de[1]);
+                    dk[(i >> 1) + 1] = f2_to_bf2(de[2], de[3]);
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -756,7 +781,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     p.dk = (__nv_bfloat16*)dk; p.dk_st = st[10]; p.dk_sh = st[11];
     p.dv = (__nv_bfloat16*)dv; p.dv_st = st[12]; p.dv_sh = st[13];
     const size_t smem_dq = 2 * TC_TILE + 4 * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
-    const size_t smem_kv = 2 * TC_TILE + 4 * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 64;
+    const size_t smem_kv = 2 * TC_TILE + 4 * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
     static bool attr = false;
     if (!attr) {
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));

@@ -11,10 +11,10 @@
 //   never written (the reference leaves them unspecified as well).
 //
 // Design: persistent kernel, one CTA per SM, warp-specialised:
-//   warp 0   TMA producer: 128x64 / 64x64 SWIZZLE_128B boxes into a 6-stage smem ring (mbarrier tx-count)
-//   warp 1   MMA issuer: one elected lane issues tcgen05.mma (M=128, N=128, K=16, cta_group::1); operands
+//   warp 0   TMA producer: SWIZZLE_128B boxes into a 4-stage smem ring of (128x64 A + 256x64 B) tiles (mbarrier tx-count)
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma (M=128, N=256, K=16, cta_group::1); operands
 //            are read from smem through UMMA descriptors (K-major or MN-major), accumulators live in TMEM
-//            (2 x 128 columns, double-buffered against the epilogue); tcgen05.commit frees smem stages and
+//            (2 x 256 columns = all of TMEM, double-buffered against the epilogue); tcgen05.commit frees smem stages and
 //            hands the accumulator over
 //   warps 2-5 epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> bf16 -> guarded global stores
 // The tile list (group, m-tile, n-tile) is derived on the device from the cumsum tensor, so no host
@@ -25,8 +25,8 @@
 
 namespace vb {
 
-constexpr int GG_BM = 128, GG_BN = 128, GG_BK = 64, GG_STAGES = 6;
-constexpr int GG_STAGE_BYTES = (GG_BM + GG_BN) * GG_BK * 2;  // 32 KB
+constexpr int GG_BM = 128, GG_BN = 256, GG_BK = 64, GG_STAGES = 4;
+constexpr int GG_STAGE_BYTES = (GG_BM + GG_BN) * GG_BK * 2;  // 48 KB (a 128x256 tile halves the L2->smem bytes per FLOP of 128x128)
 constexpr int GG_MAX_G = 1024;
 constexpr int GG_THREADS = 192;
 
@@ -112,11 +112,7 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
-    if (warp == 1) {  // TMEM: 256 columns = two 128-column fp32 accumulators
-        const uint32_t ncols = 256;
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * GG_BN);  // two fp32 accumulators of GG_BN columns
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -139,15 +135,17 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const int kr = ti.row0 + kb * GG_BK;
                         tma_load_2d(sa, &tmA, ti.mt * GG_BM, kr, &full[s]);
                         tma_load_2d(sa + GG_BK * 128, &tmA, ti.mt * GG_BM + 64, kr, &full[s]);
-                        tma_load_2d(sb, &tmB, ti.nt * GG_BN, kr, &full[s]);
-                        tma_load_2d(sb + GG_BK * 128, &tmB, ti.nt * GG_BN + 64, kr, &full[s]);
+#pragma unroll
+                        for (int i = 0; i < GG_BN / 64; ++i)
+                            tma_load_2d(sb + i * GG_BK * 128, &tmB, ti.nt * GG_BN + i * 64, kr, &full[s]);
                     } else {
                         tma_load_2d(sa, &tmA, kb * GG_BK, ti.row0, &full[s]);
                         if (MODE == GG_NT) {
                             tma_load_3d(sb, &tmB, kb * GG_BK, ti.nt * GG_BN, ti.g, &full[s]);
                         } else {
-                            tma_load_3d(sb, &tmB, ti.nt * GG_BN, kb * GG_BK, ti.g, &full[s]);
-                            tma_load_3d(sb + GG_BK * 128, &tmB, ti.nt * GG_BN + 64, kb * GG_BK, ti.g, &full[s]);
+#pragma unroll
+                            for (int i = 0; i < GG_BN / 64; ++i)
+                                tma_load_3d(sb + i * GG_BK * 128, &tmB, ti.nt * GG_BN + i * 64, kb * GG_BK, ti.g, &full[s]);
                         }
                     }
                     if (++s == GG_STAGES) { s = 0; ph ^= 1; }
@@ -260,8 +258,7 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        const uint32_t ncols = 256;
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+        tmem_dealloc(tmem_base, 2 * GG_BN);
     }
 }
 
