@@ -196,13 +196,14 @@ def run_b200(args) -> None:
     if rank == 0:
         sampler.start()
     _lib.reset_launch_count()
-    vattn.PROFILE = []  # CUDA-event pairs around every attention forward launch (the dominant kernel of ours)
+    # CUDA-event pairs around every launch of the three attention kernels (the heaviest kernels of ours)
+    vattn.PROFILE = {"fwd": [], "bwd_dq": [], "bwd_dkdv": []}
     ms_dev, loss_dev = timed(args.steps, e2e=False)
     launches = _lib.launch_count()
     prof = vattn.PROFILE
     vattn.PROFILE = None
     torch.cuda.synchronize()
-    attn_ms = [a.elapsed_time(b) for a, b in prof]
+    prof_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in prof.items()}
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
     clocks = sampler.stop() if rank == 0 else {}
     mem_gb = torch.cuda.max_memory_allocated() / 2**30
@@ -212,7 +213,15 @@ def run_b200(args) -> None:
         tokens = SEQ_LEN * world
         value = tokens / (ms_dev / 1e3)
         fpt = flops_per_token(cfg, [SEQ_LEN])
-        attn_flops = 4 * SEQ_LEN * SEQ_LEN * cfg.head_dim * cfg.num_attention_heads / 2  # causal fwd per launch
+        fwd_flops = 4 * SEQ_LEN * SEQ_LEN * cfg.head_dim * cfg.num_attention_heads / 2  # causal fwd per launch
+        # algorithmic FLOPs per launch: fwd = 2 matmuls, dQ = 1, dK+dV = 2 of the 5 backward matmuls
+        kinfo = {"fwd": ("attn_fwd_tc_kernel (varlen causal attention forward, tcgen05)", fwd_flops),
+                 "bwd_dkdv": ("attn_bwd_dkdv_tc_kernel (attention backward dK/dV, tcgen05)", fwd_flops * 2.5 * 0.6),
+                 "bwd_dq": ("attn_bwd_dq_tc_kernel (attention backward dQ, tcgen05)", fwd_flops * 2.5 * 0.4)}
+        totals = {k: sum(v) for k, v in prof_ms.items() if v}
+        dom = max(totals, key=totals.get) if totals else "fwd"
+        attn_ms = prof_ms.get(dom, [])
+        attn_flops = kinfo[dom][1]
         attn_avg_ms = sum(attn_ms) / max(1, len(attn_ms))
         achieved = attn_flops / (attn_avg_ms * 1e-3) / 1e12 if attn_ms else None
         out = {
@@ -231,7 +240,8 @@ def run_b200(args) -> None:
             "e2e": {"value": round(tokens / (ms_e2e / 1e3), 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 2)},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "attn_fwd_kernel<128> (varlen causal attention forward, 72 launches/step)",
+            "roofline": {"kernel": kinfo[dom][0] + f", {len(attn_ms) // max(1, args.steps)} launches/step",
+                         "attention_ms_per_step": {k: round(v / max(1, args.steps), 2) for k, v in totals.items()},
                          "bound": "tensor", "achieved": round(achieved, 1) if achieved else None,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16_tflops_sustained"], 4) if achieved else None,

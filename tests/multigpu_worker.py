@@ -123,6 +123,44 @@ def test_fsdp(rank, world, dev):
         torch.testing.assert_close(got, ref[n], atol=1e-6, rtol=1e-4, msg=lambda s, n=n: f"fsdp grad {n}: {s}")
 
 
+def test_ulysses_model(rank, world, dev):
+    """Toy Qwen3 through the host caller with Ulysses SP over all ranks vs the reference fixture (loss, grad-norm)."""
+    from veomni_b200.host_qwen3 import Qwen3Config, Qwen3ForCausalLM
+
+    f = torch.load(REPO / "tests" / "golden" / "qwen3_toy.pt", weights_only=False)
+    cfg = Qwen3Config.from_hf_dict(f["config"])
+    if cfg.num_attention_heads % world or sum(f["seq_lens"]) % world:
+        return
+    model = Qwen3ForCausalLM(cfg)
+    model.load_state_dict(f["state_dict"])
+    model = model.to(dev).to(torch.bfloat16)
+    model.sp_group = dist.group.WORLD
+    model.train()
+    lens = f["seq_lens"]
+    T = sum(lens)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    # SequenceParallelCollator (veomni/data/data_collator.py:336-389): shift labels on the full row, then slice
+    shift = torch.nn.functional.pad(f["labels"], (0, 1), value=-100)[..., 1:]
+    sl = slice(rank * T // world, (rank + 1) * T // world)
+    ids, pos, sh = f["input_ids"][:, sl].to(dev), f["position_ids"][:, sl].to(dev), shift[:, sl].to(dev)
+    loss_local = model(ids, pos, cu, max(lens), shift_labels=sh)
+    n_local = (sh != -100).sum().float()
+    n_tot = n_local.clone()
+    dist.all_reduce(n_tot)
+    (loss_local * n_local / n_tot).backward()
+    loss = (loss_local.detach().float() * n_local / n_tot)
+    dist.all_reduce(loss)
+    ref = float(f["loss"])
+    assert abs(float(loss) - ref) / ref < 2e-2, (float(loss), ref)
+    sq = torch.zeros((), device=dev)
+    for p_ in model.parameters():
+        g = p_.grad.float()
+        dist.all_reduce(g)  # every rank holds the full weights: SP grads add up
+        sq += (g * g).sum()
+    gn = float(sq.sqrt())
+    assert abs(gn - float(f["grad_norm"])) / float(f["grad_norm"]) < 5e-2, (gn, float(f["grad_norm"]))
+
+
 def test_ep(rank, world, dev):
     """EP dispatch/combine + expert MLP vs the oracle (and vs the reference run stored in tests/golden/multirank.pt)."""
     from oracle import moe as o_moe
@@ -286,6 +324,7 @@ def main():
     stage("ulysses", test_ulysses, rank, world, dev)
     stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
     stage("expert parallel dispatch/combine", test_ep, rank, world, dev)
+    stage("ulysses SP through the model (reference fixture)", test_ulysses_model, rank, world, dev)
     if a.bench:
         stage("bench", bench, symm, rank, world, dev)
     dist.barrier()

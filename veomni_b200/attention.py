@@ -14,13 +14,33 @@ from . import _lib
 from ._lib import VB200Error, check, stream_ptr
 
 
-# When set to a list, every forward launch appends a (start, end) CUDA-event pair recorded on the
-# launching stream (bench.py uses it for the live per-launch duration of the dominant kernel).
+# When set to a dict {"fwd": [], "bwd_dq": [], "bwd_dkdv": []}, every launch of the corresponding kernel appends a
+# (start, end) CUDA-event pair recorded on the launching stream (bench.py: live per-launch durations).  A list is
+# accepted for the forward kernel only.
 PROFILE = None
 
+
+def _prof(tag):
+    if PROFILE is None:
+        return None
+    lst = PROFILE if isinstance(PROFILE, list) and tag == "fwd" else (PROFILE.get(tag) if isinstance(PROFILE, dict) else None)
+    if lst is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return lst, ev
+
+
+def _prof_end(h):
+    if h is not None:
+        lst, ev0 = h
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        lst.append((ev0, ev1))
+
 # Forward implementation for head_dim 128: "tc" = tcgen05/TMEM pipeline (attention_tc.cu), "mma" = mma.sync kernel.
-FWD_IMPL = os.environ.get("VB200_ATTN_FWD", "mma")
-BWD_IMPL = os.environ.get("VB200_ATTN_BWD", "mma")
+FWD_IMPL = os.environ.get("VB200_ATTN_FWD", "tc")
+BWD_IMPL = os.environ.get("VB200_ATTN_BWD", "tc")
 
 
 def _strides(*tensors):
@@ -62,19 +82,14 @@ class _VarlenAttn(torch.autograd.Function):
         lse = torch.empty(Hq, T, dtype=torch.float32, device=q.device)
         lib = _lib.load()
         with torch.cuda.device(q.device):
-            if PROFILE is not None:
-                ev0 = torch.cuda.Event(enable_timing=True)
-                ev0.record()
+            hprof = _prof("fwd")
             fwd = lib.vb200_attn_varlen_fwd_tc if (FWD_IMPL == "tc" and D == 128) else lib.vb200_attn_varlen_fwd
             check(
                 fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), cu.data_ptr(), nseq,
                     int(max_seqlen), T, Hq, Hk, D, _strides(q, k, v, o), scale, 1 if causal else 0, stream_ptr()),
                 "vb200_attn_varlen_fwd",
             )
-            if PROFILE is not None:
-                ev1 = torch.cuda.Event(enable_timing=True)
-                ev1.record()
-                PROFILE.append((ev0, ev1))
+            _prof_end(hprof)
         ctx.save_for_backward(q, k, v, o, lse, cu)
         ctx.meta = (int(max_seqlen), scale, bool(causal))
         ctx.mark_non_differentiable(lse)
@@ -96,11 +111,15 @@ class _VarlenAttn(torch.autograd.Function):
             with torch.cuda.device(q.device):
                 check(lib.vb200_attn_bwd_delta(o.data_ptr(), dout.data_ptr(), delta.data_ptr(), T, Hq, D, o.stride(0), o.stride(1),
                                                dout.stride(0), dout.stride(1), stream_ptr()), "vb200_attn_bwd_delta")
-                check(lib.vb200_attn_varlen_bwd_tc(q.data_ptr(), k.data_ptr(), v.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-                                                   delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), cu.data_ptr(),
-                                                   cu.numel() - 1, max_seqlen, T, Hq, Hk, D,
-                                                   _strides(q, k, v, dout, dq, dk, dv), scale, 1 if causal else 0,
-                                                   stream_ptr()), "vb200_attn_varlen_bwd_tc")
+                strides = _strides(q, k, v, dout, dq, dk, dv)
+                for tag, only in (("bwd_dq", 1), ("bwd_dkdv", 2)) if isinstance(PROFILE, dict) else ((None, 0),):
+                    hprof = _prof(tag) if tag else None
+                    check(lib.vb200_attn_varlen_bwd_tc(q.data_ptr(), k.data_ptr(), v.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                                       delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                                                       cu.data_ptr(), cu.numel() - 1, max_seqlen, T, Hq, Hk, D, strides, scale,
+                                                       (1 if causal else 0) | (only << 8), stream_ptr()),
+                          "vb200_attn_varlen_bwd_tc")
+                    _prof_end(hprof)
             return dq, dk, dv, None, None, None, None, None
         with torch.cuda.device(q.device):
             check(

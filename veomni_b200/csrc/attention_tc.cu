@@ -28,6 +28,7 @@ struct AttnTcParams {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_D = 128;
 constexpr int TC_TILE = TC_BM * TC_D * 2;  // 32 KB
+constexpr int TC_VSTAGES = 3;              // V is held until PV_j retires (one tile later than K): deeper ring
 constexpr float kLog2eTc = 1.4426950408889634f;
 
 // Row max of a 128-column S tile held in registers; MASK applies the causal / sequence-end mask in place.
@@ -49,8 +50,8 @@ __device__ __forceinline__ float tile_row_max(uint32_t (&sv)[4][32], int n0, int
 }
 
 enum {  // barrier indices
-    B_Q = 0, B_KFULL = 1, B_VFULL = 3, B_KEMPTY = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11, B_PFULL = 13,
-    B_PVDONE = 14, B_COUNT = 15
+    B_Q = 0, B_KFULL = 1, B_VFULL = 3, B_KEMPTY = 6, B_VEMPTY = 8, B_SFULL = 11, B_SEMPTY = 13, B_PFULL = 15,
+    B_PVDONE = 16, B_COUNT = 17
 };
 
 // Forward v2 (FA4-style data flow): O stays resident in TMEM for the whole KV sweep (the PV MMAs accumulate
@@ -63,8 +64,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TC_TILE;          // 2 stages
-    uint8_t* sV = sK + 2 * TC_TILE;      // 2 stages
-    uint8_t* sP = sV + 2 * TC_TILE;
+    uint8_t* sV = sK + 2 * TC_TILE;      // TC_VSTAGES stages
+    uint8_t* sP = sV + TC_VSTAGES * TC_TILE;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sP + TC_TILE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,10 +107,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_expect_tx(&bar[B_KFULL + st], TC_TILE);
                 tma_load_3d(sK + st * TC_TILE, &tmK, 0, hk, s0 + j * TC_BN, &bar[B_KFULL + st]);
                 tma_load_3d(sK + st * TC_TILE + TC_BN * 128, &tmK, 64, hk, s0 + j * TC_BN, &bar[B_KFULL + st]);
-                mbar_wait(&bar[B_VEMPTY + st], ph ^ 1);
-                mbar_expect_tx(&bar[B_VFULL + st], TC_TILE);
-                tma_load_3d(sV + st * TC_TILE, &tmV, 0, hk, s0 + j * TC_BN, &bar[B_VFULL + st]);
-                tma_load_3d(sV + st * TC_TILE + TC_BN * 128, &tmV, 64, hk, s0 + j * TC_BN, &bar[B_VFULL + st]);
+                const int vs = j % TC_VSTAGES;
+                const uint32_t vph = (uint32_t)(j / TC_VSTAGES) & 1u;
+                mbar_wait(&bar[B_VEMPTY + vs], vph ^ 1);
+                mbar_expect_tx(&bar[B_VFULL + vs], TC_TILE);
+                tma_load_3d(sV + vs * TC_TILE, &tmV, 0, hk, s0 + j * TC_BN, &bar[B_VFULL + vs]);
+                tma_load_3d(sV + vs * TC_TILE + TC_BN * 128, &tmV, 64, hk, s0 + j * TC_BN, &bar[B_VFULL + vs]);
             }
         }
     } else if (warp == 1) {
@@ -139,20 +142,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 __syncwarp();
             }
             if (j >= 1) {  // O += P_{j-1} V_{j-1}
-                const int i = j - 1, st = i & 1;
-                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                mbar_wait(&bar[B_VFULL + st], ph);
+                const int i = j - 1, vs = i % TC_VSTAGES;
+                const uint32_t vph = (uint32_t)(i / TC_VSTAGES) & 1u;
+                mbar_wait(&bar[B_VFULL + vs], vph);
                 mbar_wait(&bar[B_PFULL], (uint32_t)i & 1u);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t v_addr = smem_u32(sV + st * TC_TILE);
+                    const uint32_t v_addr = smem_u32(sV + vs * TC_TILE);
 #pragma unroll
                     for (int k = 0; k < TC_BN / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
                         umma_f16(tmem + 256, umma_desc(p_addr + a_off, 16, 1024),
                                  umma_desc(v_addr + k * 16 * 128, TC_BN * 128, 1024), idesc_pv, (i | k) ? 1u : 0u);
                     }
-                    umma_commit(&bar[B_VEMPTY + st]);
+                    umma_commit(&bar[B_VEMPTY + vs]);
                     umma_commit(&bar[B_PVDONE]);
                 }
                 __syncwarp();
@@ -287,8 +290,10 @@ constexpr int TB_N = 64;                      // streamed tile rows
 constexpr int TB_SMALL = TB_N * TC_D * 2;     // 16 KB: a [64][128] bf16 tile (two 8 KB boxes)
 constexpr int TB_DS = 128 * TB_N * 2;         // 16 KB: a [128][64] bf16 tile (one box)
 
-enum { Q_LOAD = 0, Q_KFULL = 1, Q_VFULL = 3, Q_KEMPTY = 5, Q_VEMPTY = 7, Q_SPFULL = 9, Q_SEMPTY = 11, Q_DSFULL = 13,
-       Q_DSEMPTY = 15, Q_DONE = 17, Q_COUNT = 18 };
+constexpr int TB_KV = 4;  // K/V smem ring depth of the dQ kernel: K_j is held from S_j until dQ_j retires, and
+                          // the refill is a ~1 us TMA round trip — 2 stages left the tensor pipe idle 75 % of the time
+enum { Q_LOAD = 0, Q_KFULL = 1, Q_VFULL = 5, Q_KEMPTY = 9, Q_VEMPTY = 13, Q_SPFULL = 17, Q_SEMPTY = 19, Q_DSFULL = 21,
+       Q_DSEMPTY = 23, Q_DONE = 25, Q_COUNT = 26 };
 
 __global__ void __launch_bounds__(192, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
@@ -297,9 +302,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;                    // 32 KB
     uint8_t* sdO = sQ + TC_TILE;           // 32 KB
-    uint8_t* sK = sdO + TC_TILE;           // 2 x 16 KB
-    uint8_t* sV = sK + 2 * TB_SMALL;       // 2 x 16 KB
-    uint8_t* sdS = sV + 2 * TB_SMALL;      // 2 x 16 KB
+    uint8_t* sK = sdO + TC_TILE;           // TB_KV x 16 KB
+    uint8_t* sV = sK + TB_KV * TB_SMALL;   // TB_KV x 16 KB
+    uint8_t* sdS = sV + TB_KV * TB_SMALL;  // 2 x 16 KB
     uint64_t* bar = reinterpret_cast<uint64_t*>(sdS + 2 * TB_DS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + Q_COUNT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -334,8 +339,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tma_load_3d(sdO + hf * TC_BM * 128, &tmdO, hf * 64, h, s0 + m0, &bar[Q_LOAD]);
             }
             for (int j = 0; j < n_tiles; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                const int st = j % TB_KV;
+                const uint32_t ph = (uint32_t)(j / TB_KV) & 1u;
                 mbar_wait(&bar[Q_KEMPTY + st], ph ^ 1);
                 mbar_expect_tx(&bar[Q_KFULL + st], TB_SMALL);
                 for (int hf = 0; hf < 2; ++hf)
@@ -353,14 +358,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(&bar[Q_LOAD], 0);
         for (int j = 0; j <= n_tiles; ++j) {
             if (j < n_tiles) {
-                const int st = j & 1;
+                const int st = j & 1;                       // TMEM S/dP buffer
                 const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+                const int ks = j % TB_KV;                   // smem K/V stage
+                const uint32_t kph = (uint32_t)(j / TB_KV) & 1u;
                 mbar_wait(&bar[Q_SEMPTY + st], ph ^ 1);
-                mbar_wait(&bar[Q_KFULL + st], ph);
-                mbar_wait(&bar[Q_VFULL + st], ph);
+                mbar_wait(&bar[Q_KFULL + ks], kph);
+                mbar_wait(&bar[Q_VFULL + ks], kph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t k_addr = smem_u32(sK + st * TB_SMALL), v_addr = smem_u32(sV + st * TB_SMALL);
+                    const uint32_t k_addr = smem_u32(sK + ks * TB_SMALL), v_addr = smem_u32(sV + ks * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
@@ -375,23 +382,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         umma_f16(tmem + 128 + st * TB_N, umma_desc(do_addr + a_off, 16, 1024), umma_desc(v_addr + b_off, 16, 1024),
                                  idesc_nt, k ? 1u : 0u);
                     }
-                    umma_commit(&bar[Q_VEMPTY + st]);
+                    umma_commit(&bar[Q_VEMPTY + ks]);
                     umma_commit(&bar[Q_SPFULL + st]);
                 }
                 __syncwarp();
             }
             if (j >= 1) {
-                const int i = j - 1, st = i & 1;
+                const int i = j - 1, st = i & 1, ks = i % TB_KV;
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
                 mbar_wait(&bar[Q_DSFULL + st], ph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t ds_addr = smem_u32(sdS + st * TB_DS), k_addr = smem_u32(sK + st * TB_SMALL);
+                    const uint32_t ds_addr = smem_u32(sdS + st * TB_DS), k_addr = smem_u32(sK + ks * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TB_N / 16; ++k)
                         umma_f16(tmem + 256, umma_desc(ds_addr + k * 32, 16, 1024),
                                  umma_desc(k_addr + k * 16 * 128, TB_N * 128, 1024), idesc_dq, (i | k) ? 1u : 0u);
-                    umma_commit(&bar[Q_KEMPTY + st]);
+                    umma_commit(&bar[Q_KEMPTY + ks]);
                     umma_commit(&bar[Q_DSEMPTY + st]);
                     if (i == n_tiles - 1) umma_commit(&bar[Q_DONE]);
                 }
@@ -488,8 +495,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
 }
 
-enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = 3, K_STFULL = 5, K_STEMPTY = 7, K_PFULL = 9, K_PEMPTY = 11, K_DONE = 13,
-       K_COUNT = 14 };
+constexpr int TB_QS = 3;  // Q/dO smem ring depth of the dK/dV kernel
+enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = 4, K_STFULL = 7, K_STEMPTY = 9, K_PFULL = 11, K_PEMPTY = 13, K_DONE = 15,
+       K_COUNT = 16 };
 
 __global__ void __launch_bounds__(192, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -498,9 +506,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sK = smem;                    // 32 KB
     uint8_t* sV = sK + TC_TILE;            // 32 KB
-    uint8_t* sQ = sV + TC_TILE;            // 2 x 16 KB
-    uint8_t* sdO = sQ + 2 * TB_SMALL;      // 2 x 16 KB
-    uint8_t* sPt = sdO + 2 * TB_SMALL;     // 2 x 16 KB
+    uint8_t* sQ = sV + TC_TILE;            // TB_QS x 16 KB
+    uint8_t* sdO = sQ + TB_QS * TB_SMALL;  // TB_QS x 16 KB
+    uint8_t* sPt = sdO + TB_QS * TB_SMALL; // 2 x 16 KB
     uint8_t* sdSt = sPt + 2 * TB_DS;       // 2 x 16 KB
     uint64_t* bar = reinterpret_cast<uint64_t*>(sdSt + 2 * TB_DS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + K_COUNT);
@@ -537,8 +545,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 tma_load_3d(sV + hf * TC_BM * 128, &tmV, hf * 64, hk, s0 + n0, &bar[K_LOAD]);
             }
             for (int jb = 0; jb < jobs; ++jb) {
-                const int st = jb & 1;
-                const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
+                const int st = jb % TB_QS;
+                const uint32_t ph = (uint32_t)(jb / TB_QS) & 1u;
                 const int hh = hk * G + jb / nq, qi = i_start + jb % nq;
                 mbar_wait(&bar[K_QEMPTY + st], ph ^ 1);
                 mbar_expect_tx(&bar[K_QFULL + st], 2 * TB_SMALL);
@@ -555,13 +563,15 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         mbar_wait(&bar[K_LOAD], 0);
         for (int jb = 0; jb <= jobs; ++jb) {
             if (jb < jobs) {
-                const int st = jb & 1;
+                const int st = jb & 1;                       // TMEM S^T/dP^T buffer
                 const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
+                const int qs = jb % TB_QS;                   // smem Q/dO stage
+                const uint32_t qph = (uint32_t)(jb / TB_QS) & 1u;
                 mbar_wait(&bar[K_STEMPTY + st], ph ^ 1);
-                mbar_wait(&bar[K_QFULL + st], ph);
+                mbar_wait(&bar[K_QFULL + qs], qph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t q_addr = smem_u32(sQ + st * TB_SMALL), do_addr = smem_u32(sdO + st * TB_SMALL);
+                    const uint32_t q_addr = smem_u32(sQ + qs * TB_SMALL), do_addr = smem_u32(sdO + qs * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
@@ -581,13 +591,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 __syncwarp();
             }
             if (jb >= 1) {
-                const int i = jb - 1, st = i & 1;
+                const int i = jb - 1, st = i & 1, qs = i % TB_QS;
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
                 mbar_wait(&bar[K_PFULL + st], ph);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t pt_addr = smem_u32(sPt + st * TB_DS), dst_addr = smem_u32(sdSt + st * TB_DS);
-                    const uint32_t q_addr = smem_u32(sQ + st * TB_SMALL), do_addr = smem_u32(sdO + st * TB_SMALL);
+                    const uint32_t q_addr = smem_u32(sQ + qs * TB_SMALL), do_addr = smem_u32(sdO + qs * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TB_N / 16; ++k)
                         umma_f16(tmem + 256, umma_desc(pt_addr + k * 32, 16, 1024),
@@ -596,7 +606,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                     for (int k = 0; k < TB_N / 16; ++k)
                         umma_f16(tmem + 384, umma_desc(dst_addr + k * 32, 16, 1024),
                                  umma_desc(q_addr + k * 16 * 128, TB_N * 128, 1024), idesc_acc, (i | k) ? 1u : 0u);
-                    umma_commit(&bar[K_QEMPTY + st]);
+                    umma_commit(&bar[K_QEMPTY + qs]);
                     umma_commit(&bar[K_PEMPTY + st]);
                     if (i == jobs - 1) umma_commit(&bar[K_DONE]);
                 }
@@ -643,26 +653,34 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
                 tmem_wait_ld();
                 uint32_t pk[16], dk[16];
+                if (need_mask) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c * 32 + i);
-                    const float4 d4 = *reinterpret_cast<const float4*>(dl_s + c * 32 + i);
-                    const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dlv[4] = {d4.x, d4.y, d4.z, d4.w};
-                    float pe[4], de[4];
+                    for (int i = 0; i < 32; i += 2) {
+                        float pe[2], de[2];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float pv = exp2f(__uint_as_float(sv[i + e]) * sl2 - lv[e]);
-                        if (need_mask) {
+                        for (int e = 0; e < 2; ++e) {
                             const int m = qi * TB_N + c * 32 + i + e;  // q index (column)
-                            if (!(n < L && m < L && (!p.causal || n <= m))) pv = 0.f;
+                            const bool ok = n < L && m < L && (!p.causal || n <= m);
+                            pe[e] = ok ? exp2f(__uint_as_float(sv[i + e]) * sl2 - lse_s[c * 32 + i + e]) : 0.f;
+                            de[e] = pe[e] * (__uint_as_float(dv[i + e]) - dl_s[c * 32 + i + e]);
                         }
-                        pe[e] = pv;
-                        de[e] = pv * (__uint_as_float(dv[i + e]) - dlv[e]);
+                        pk[i >> 1] = f2_to_bf2(pe[0], pe[1]);
+                        dk[i >> 1] = f2_to_bf2(de[0], de[1]);
                     }
-                    pk[i >> 1] = f2_to_bf2(pe[0], pe[1]);
-                    pk[(i >> 1) + 1] = f2_to_bf2(pe[2], pe[3]);
-                    dk[i >> 1] = f2_to_bf2(de[0], de[1]);
-                    dk[(i >> 1) + 1] = f2_to_bf2(de[2], de[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c * 32 + i);
+                        const float4 d4 = *reinterpret_cast<const float4*>(dl_s + c * 32 + i);
+                        const float p0 = exp2f(__uint_as_float(sv[i + 0]) * sl2 - l4.x);
+                        const float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - l4.y);
+                        const float p2 = exp2f(__uint_as_float(sv[i + 2]) * sl2 - l4.z);
+                        const float p3 = exp2f(__uint_as_float(sv[i + 3]) * sl2 - l4.w);
+                        pk[i >> 1] = f2_to_bf2(p0, p1);
+                        pk[(i >> 1) + 1] = f2_to_bf2(p2, p3);
+                        dk[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(dv[i + 0]) - d4.x), p1 * (__uint_as_float(dv[i + 1]) - d4.y));
+                        dk[(i >> 1) + 1] = f2_to_bf2(p2 * (__uint_as_float(dv[i + 2]) - d4.z), p3 * (__uint_as_float(dv[i + 3]) - d4.w));
+                    }
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -738,7 +756,7 @@ extern "C" int vb200_attn_varlen_fwd_tc(const void* q, const void* k, const void
     AttnTcParams p{};
     p.cu_seqlens = cu_seqlens; p.Hq = q_heads; p.Hk = k_heads; p.total = total; p.scale = scale; p.causal = causal;
     p.o = (__nv_bfloat16*)o; p.o_stride_tok = st[6]; p.o_stride_head = st[7]; p.lse = lse;
-    const size_t smem = 6 * TC_TILE + B_COUNT * 8 + 16 + 64;
+    const size_t smem = (4 + TC_VSTAGES) * TC_TILE + B_COUNT * 8 + 16 + 64;
     static bool attr = false;
     if (!attr) {
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -758,7 +776,10 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
                                         int32_t num_seqs, int32_t max_seqlen, int32_t total, int32_t q_heads,
                                         int32_t k_heads, int32_t head_dim, const int64_t* st, float scale, int32_t causal,
                                         void* stream) {
-    // st: (tok, head) strides of q, k, v, dout, dq, dk, dv
+    // st: (tok, head) strides of q, k, v, dout, dq, dk, dv.  causal bit 0 = causal; bits 8/9 = run only the
+    // dQ / only the dK-dV kernel (used to time the two kernels separately; 0 = both).
+    const int only = (causal >> 8) & 3;
+    causal &= 1;
     if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: head_dim must be 128");
     if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: Hq % Hk != 0");
     for (int i = 0; i < 14; ++i)
@@ -780,8 +801,8 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     p.dq = (__nv_bfloat16*)dq; p.dq_st = st[8]; p.dq_sh = st[9];
     p.dk = (__nv_bfloat16*)dk; p.dk_st = st[10]; p.dk_sh = st[11];
     p.dv = (__nv_bfloat16*)dv; p.dv_st = st[12]; p.dv_sh = st[13];
-    const size_t smem_dq = 2 * TC_TILE + 4 * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
-    const size_t smem_kv = 2 * TC_TILE + 4 * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
+    const size_t smem_dq = 2 * TC_TILE + 2 * TB_KV * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
+    const size_t smem_kv = 2 * TC_TILE + 2 * TB_QS * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
     static bool attr = false;
     if (!attr) {
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
@@ -790,11 +811,16 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     }
     cudaStream_t s = (cudaStream_t)stream;
     dim3 gq((max_seqlen + TC_BM - 1) / TC_BM, q_heads, num_seqs);
-    attn_bwd_dq_tc_kernel<<<gq, 192, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
-    VB_HOST_CHECK_LAUNCH();
+    if (only != 2) {
+        attn_bwd_dq_tc_kernel<<<gq, 192, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        vb200_count_launch(1);
+        VB_HOST_CHECK_LAUNCH();
+    }
     dim3 gk((max_seqlen + TC_BM - 1) / TC_BM, k_heads, num_seqs);
-    attn_bwd_dkdv_tc_kernel<<<gk, 192, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
-    vb200_count_launch(2);
+    if (only != 1) {
+        attn_bwd_dkdv_tc_kernel<<<gk, 192, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+        vb200_count_launch(1);
+    }
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
 }
