@@ -35,6 +35,7 @@ def parse_args():
     ap.add_argument("--train.accelerator.ulysses_size", dest="ulysses_size", type=int, default=1)
     ap.add_argument("--train.enable_gradient_checkpointing", dest="ckpt", type=int, default=1)
     ap.add_argument("--train.output_dir", dest="output_dir", default="")
+    ap.add_argument("--model.num_hidden_layers", dest="layers", type=int, default=0, help="override (debug / smoke runs)")
     return ap.parse_args()
 
 
@@ -59,6 +60,8 @@ def main():
         cfg = Qwen3Config.qwen3_8b()
     else:
         cfg = Qwen3Config.from_hf_dict(json.loads((Path(a.config_path) / "config.json").read_text()))
+    if a.layers:
+        cfg.num_hidden_layers = a.layers
     with torch.device("meta"):
         model = Qwen3ForCausalLM(cfg)
     model.to_empty(device=dev)

@@ -96,28 +96,57 @@ def bench_rmsnorm(dev, iters):
 
 
 def bench_rope(dev, iters):
+    """Direct C-ABI calls with preallocated buffers (the Python autograd wrappers cost more CPU time than these kernels)."""
     T, Hq, Hk, D = 4096, 32, 8, 128
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
     cos = torch.randn(T, D, device=dev, dtype=BF)
     sin = torch.randn(T, D, device=dev, dtype=BF)
-    sets = [(torch.randn(T, Hq, D, device=dev, dtype=BF), torch.randn(T, Hk, D, device=dev, dtype=BF)) for _ in range(6)]
     wq = torch.ones(D, device=dev, dtype=BF)
+    sets = []
+    for _ in range(6):
+        q, k = torch.randn(T, Hq, D, device=dev, dtype=BF), torch.randn(T, Hk, D, device=dev, dtype=BF)
+        sets.append((q, k, torch.empty_like(q), torch.empty_like(k), torch.empty(T, Hq, device=dev), torch.empty(T, Hk, device=dev)))
+    nbytes = 2 * T * (Hq + Hk) * D * 2
 
-    def rope(q, k):
-        F.apply_rotary_pos_emb(q[None].transpose(1, 2), k[None].transpose(1, 2), cos[None], sin[None])
+    def rope(q, k, qo, ko, rq, rk):
+        lib.vb200_rope(q.data_ptr(), qo.data_ptr(), k.data_ptr(), ko.data_ptr(), cos.data_ptr(), sin.data_ptr(), T, Hq, Hk, D,
+                       Hq * D, D, Hk * D, D, Hq * D, D, Hk * D, D, 0, st)
 
-    report("rope_qk[4096x(32+8)x128]", time_fn(rope, sets, iters), nbytes=2 * T * (Hq + Hk) * D * 2)
+    report("rope_qk[4096x(32+8)x128]", time_fn(rope, sets, iters), nbytes=nbytes)
 
-    def fused(q, k):
-        F.qknorm_rope(q, k, wq, wq, cos, sin, 1e-6)
+    def fused(q, k, qo, ko, rq, rk):
+        lib.vb200_qknorm_rope_fwd(q.data_ptr(), k.data_ptr(), wq.data_ptr(), wq.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+                                  qo.data_ptr(), ko.data_ptr(), rq.data_ptr(), rk.data_ptr(), T, Hq, Hk, D, 1e-6, st)
 
-    report("qknorm_rope_fwd[4096x(32+8)x128]", time_fn(fused, sets, iters), nbytes=2 * T * (Hq + Hk) * D * 2)
+    report("qknorm_rope_fwd[4096x(32+8)x128]", time_fn(fused, sets, iters), nbytes=nbytes)
+    part = torch.empty(lib.vb200_qknorm_rope_bwd_partials(T), 2 * D, device=dev)
+    dwq, dwk = torch.empty(D, device=dev), torch.empty(D, device=dev)
+
+    def fused_bwd(q, k, qo, ko, rq, rk):
+        lib.vb200_qknorm_rope_bwd(qo.data_ptr(), ko.data_ptr(), q.data_ptr(), k.data_ptr(), wq.data_ptr(), wq.data_ptr(),
+                                  cos.data_ptr(), sin.data_ptr(), rq.data_ptr(), rk.data_ptr(), qo.data_ptr(), ko.data_ptr(),
+                                  part.data_ptr(), dwq.data_ptr(), dwk.data_ptr(), T, Hq, Hk, D, st)
+
+    report("qknorm_rope_bwd[4096x(32+8)x128]", time_fn(fused_bwd, sets, iters), nbytes=3 * T * (Hq + Hk) * D * 2)
 
 
 def bench_swiglu(dev, iters):
     T, I = 4096, 12288
-    sets = [(torch.randn(T, I, device=dev, dtype=BF), torch.randn(T, I, device=dev, dtype=BF)) for _ in range(3)]
-    with torch.no_grad():
-        report("swiglu_fwd[4096x12288]", time_fn(lambda g, u: F.silu_mul(g, u), sets, iters), nbytes=3 * T * I * 2)
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    sets = [(torch.randn(T, I, device=dev, dtype=BF), torch.randn(T, I, device=dev, dtype=BF), torch.empty(T, I, device=dev, dtype=BF),
+             torch.empty(T, I, device=dev, dtype=BF)) for _ in range(2)]
+
+    def fwd(g, u, o, o2):
+        lib.vb200_swiglu_fwd(g.data_ptr(), u.data_ptr(), o.data_ptr(), T, I, I, I, st)
+
+    report("swiglu_fwd[4096x12288]", time_fn(fwd, sets, iters), nbytes=3 * T * I * 2)
+
+    def bwd(g, u, o, o2):
+        lib.vb200_swiglu_bwd(o.data_ptr(), g.data_ptr(), u.data_ptr(), o.data_ptr(), o2.data_ptr(), T, I, I, I, I, st)
+
+    report("swiglu_bwd[4096x12288]", time_fn(bwd, sets, iters), nbytes=5 * T * I * 2)
 
 
 BENCHES = {"rmsnorm": bench_rmsnorm, "rope": bench_rope, "swiglu": bench_swiglu}

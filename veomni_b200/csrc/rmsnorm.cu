@@ -14,7 +14,7 @@
 // STAGES row buffers in shared memory filled by 1-D bulk-async copies (TMA engine, SASS UBLKCP)
 // that complete on an mbarrier; the warp reduces sum(x^2) with shuffles, overwrites the row in
 // place with the normalised bf16 values and hands the buffer back to the TMA engine with a
-// bulk shared->global store. No register staging of the row, 3 rows in flight per warp.
+// bulk shared->global store. No register staging of the row, 2 rows in flight per warp, 12 warps per SM.
 // Forward, narrow rows (cols <= 256, e.g. per-head q/k norm): a group of lanes per row.
 // Backward: threads own columns and walk over rows, so dw accumulates in registers; one
 // __syncthreads per row (double-buffered partials), deterministic two-pass dw reduction.
@@ -25,9 +25,10 @@ namespace vb {
 // ------------------------------------------------------------------------------------------
 // forward, bulk-async staged
 // ------------------------------------------------------------------------------------------
-constexpr int kFwdStages = 3;
+constexpr int kFwdStages = 2;   // rows in flight per warp
+constexpr int kFwdMaxWarps = 12; // 12 warps x 2 stages x 8 KB (H = 4096) fills the SM's shared memory
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kFwdMaxWarps * 32, 1)
 rmsnorm_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                         __nv_bfloat16* __restrict__ y, float* __restrict__ rstd, int64_t rows, int cols,
                         float eps, int warps_per_cta) {
@@ -295,13 +296,24 @@ rmsnorm_bwd_small_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
     }
 }
 
-__global__ void colsum_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t nparts,
-                              int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+// out[c] = sum_p partial[p][c].  Block (32 columns x 8 partial-lanes): coalesced 128-byte rows, 8 independent
+// accumulation chains per column, combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t nparts, int cols) {
+    __shared__ float red[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
     float t = 0.f;
-    for (int64_t p = 0; p < nparts; ++p) t += partial[p * cols + c];
-    out[c] = t;
+    if (c < cols)
+        for (int64_t p = y; p < nparts; p += 8) t += partial[p * cols + c];
+    red[y][x] = t;
+    __syncthreads();
+    if (y == 0 && c < cols) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a += red[i][x];
+        out[c] = a;
+    }
 }
 
 static int bwd_grid(int64_t rows, int cols) {
@@ -350,7 +362,7 @@ extern "C" int vb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* r
     } else {
         const size_t row_bytes = (size_t)cols * 2;
         int warps = (int)((200 * 1024 - row_bytes) / (row_bytes * kFwdStages));
-        if (warps > 8) warps = 8;
+        if (warps > kFwdMaxWarps) warps = kFwdMaxWarps;
         if (warps < 1) return vb200_set_error(VB200_EINVAL, "rmsnorm_fwd: row too wide for smem staging");
         const size_t smem = row_bytes * (1 + (size_t)warps * kFwdStages) + sizeof(uint64_t) * warps * kFwdStages;
         static bool attr_set = false;
@@ -405,7 +417,7 @@ extern "C" int vb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, c
 #undef SMALL
 #undef WIDE
     VB_HOST_CHECK_LAUNCH();
-    colsum_kernel<<<(int)((cols + 255) / 256), 256, 0, st>>>(dw_partial, dw, g, (int)cols);
+    colsum_kernel<<<(int)((cols + 31) / 32), 256, 0, st>>>(dw_partial, dw, g, (int)cols);
     vb200_count_launch(2);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;

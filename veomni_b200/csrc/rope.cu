@@ -289,14 +289,24 @@ qknorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq_out, const __nv_bflo
     }
 }
 
-__global__ void colsum2_kernel(const float* __restrict__ partial, float* __restrict__ out_a,
-                               float* __restrict__ out_b, int64_t nparts, int D) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 2 * D) return;
+__global__ void __launch_bounds__(256)
+colsum2_kernel(const float* __restrict__ partial, float* __restrict__ out_a, float* __restrict__ out_b, int64_t nparts,
+               int D) {
+    __shared__ float red[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + x;
     float t = 0.f;
-    for (int64_t p = 0; p < nparts; ++p) t += partial[p * 2 * D + c];
-    if (c < D) out_a[c] = t;
-    else out_b[c - D] = t;
+    if (c < 2 * D)
+        for (int64_t p = y; p < nparts; p += 8) t += partial[p * 2 * D + c];
+    red[y][x] = t;
+    __syncthreads();
+    if (y == 0 && c < 2 * D) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a += red[i][x];
+        if (c < D) out_a[c] = a;
+        else out_b[c - D] = a;
+    }
 }
 
 static int items_grid(int64_t tokens, int H, int lph, int max_ctas) {
@@ -395,7 +405,7 @@ extern "C" int vb200_qknorm_rope_bwd(const void* dq_out, const void* dk_out, con
     else GO(16);
 #undef GO
     VB_HOST_CHECK_LAUNCH();
-    colsum2_kernel<<<(2 * head_dim + 255) / 256, 256, 0, st>>>(dw_partial, dwq, dwk, g, head_dim);
+    colsum2_kernel<<<(2 * head_dim + 31) / 32, 256, 0, st>>>(dw_partial, dwq, dwk, g, head_dim);
     vb200_count_launch(2);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
