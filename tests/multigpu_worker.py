@@ -161,6 +161,51 @@ def test_ulysses_model(rank, world, dev):
     assert abs(gn - float(f["grad_norm"])) / float(f["grad_norm"]) < 5e-2, (gn, float(f["grad_norm"]))
 
 
+def test_ep_model(rank, world, dev):
+    """Toy Qwen3-MoE through the host caller: EP over all ranks (ParallelPlan slicing + NVLink dispatch/combine)
+    vs the same model without EP on the same tokens — loss and hidden-state gradients must agree."""
+    from veomni_b200 import moe as M
+    from veomni_b200.ep import EPContext
+    from veomni_b200.host_qwen3_moe import Qwen3MoeConfig, Qwen3MoeForCausalLM
+
+    cfg = Qwen3MoeConfig(vocab_size=256, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, head_dim=64, num_experts=4 * world, num_experts_per_tok=2,
+                         moe_intermediate_size=128)
+    torch.manual_seed(0)
+    ref = Qwen3MoeForCausalLM(cfg).to(dev)
+    ref.init_weights(seed=0)
+    ref = ref.to(torch.bfloat16)
+    ep_model = Qwen3MoeForCausalLM(cfg).to(dev).to(torch.bfloat16)
+    ep_model.load_state_dict(ref.state_dict())
+    ep_model.get_parallel_plan().apply(ep_model, ep_size=world, ep_rank=rank)
+    assert ep_model.model.layers[0].mlp.experts.gate_up_proj.shape[0] == 4
+    g = torch.Generator().manual_seed(50 + rank)
+    lens = [70, 58]
+    ids = torch.randint(0, 256, (1, sum(lens)), generator=g).to(dev)
+    pos = torch.cat([torch.arange(n) for n in lens])[None].to(dev)
+    cu = torch.tensor([0, 70, 128], dtype=torch.int32, device=dev)
+    ref.train(); ep_model.train()
+    M.set_ep_group(None)
+    loss_ref = ref(ids, pos, cu, 70, labels=ids)
+    loss_ref.backward()
+    M.set_ep_group(EPContext())
+    try:
+        loss_ep = ep_model(ids, pos, cu, 70, labels=ids)
+        loss_ep.backward()
+    finally:
+        M.set_ep_group(None)
+    torch.testing.assert_close(loss_ep.float(), loss_ref.float(), atol=2e-2, rtol=2e-2)
+    ga, gb = ep_model.model.embed_tokens.weight.grad.float(), ref.model.embed_tokens.weight.grad.float()
+    s = max(1e-6, float(gb.abs().max()))
+    torch.testing.assert_close(ga / s, gb / s, atol=5e-2, rtol=5e-2)
+    # expert weight grads: the EP rank's slice equals the sum over ranks of the non-EP grads for those experts
+    full = ref.model.layers[0].mlp.experts.down_proj.grad.float().clone()
+    dist.all_reduce(full)
+    mine = ep_model.model.layers[0].mlp.experts.down_proj.grad.float()
+    s = max(1e-6, float(full.abs().max()))
+    torch.testing.assert_close(mine / s, full[rank * 4 : (rank + 1) * 4] / s, atol=5e-2, rtol=5e-2)
+
+
 def test_ep(rank, world, dev):
     """EP dispatch/combine + expert MLP vs the oracle (and vs the reference run stored in tests/golden/multirank.pt)."""
     from oracle import moe as o_moe
@@ -325,6 +370,7 @@ def main():
     stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
     stage("expert parallel dispatch/combine", test_ep, rank, world, dev)
     stage("ulysses SP through the model (reference fixture)", test_ulysses_model, rank, world, dev)
+    stage("expert parallel through the Qwen3-MoE caller", test_ep_model, rank, world, dev)
     if a.bench:
         stage("bench", bench, symm, rank, world, dev)
     dist.barrier()

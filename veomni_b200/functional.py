@@ -157,7 +157,7 @@ def apply_rotary_pos_emb(q, k, cos, sin, position_ids=None, unsqueeze_dim: int =
 # ----------------------------------------------------------------------------------------------
 class _QKNormRope(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, wq, wk, cos, sin, eps):
+    def forward(ctx, q, k, wq, wk, cos, sin, eps, out=None):
         # q: [T, Hq, D], k: [T, Hk, D] contiguous; cos/sin: [T, D]
         _need_cuda_bf16(q, k)
         q = _aligned(q.contiguous())
@@ -168,7 +168,12 @@ class _QKNormRope(torch.autograd.Function):
         wk_b = wk.detach().to(torch.bfloat16).contiguous()
         cos = cos.to(torch.bfloat16).contiguous()
         sin = sin.to(torch.bfloat16).contiguous()
-        q_out, k_out = torch.empty_like(q), torch.empty_like(k)
+        if out is not None:  # e.g. views of the Ulysses staging buffer: the exchange then needs no copy-in
+            q_out, k_out = out
+            if q_out.shape != q.shape or k_out.shape != k.shape or not (q_out.is_contiguous() and k_out.is_contiguous()):
+                raise VB200Error("qknorm_rope: `out` tensors must be contiguous and shaped like q / k")
+        else:
+            q_out, k_out = torch.empty_like(q), torch.empty_like(k)
         rq = torch.empty(T, Hq, dtype=torch.float32, device=q.device)
         rk = torch.empty(T, Hk, dtype=torch.float32, device=q.device)
         lib = _lib.load()
@@ -204,12 +209,13 @@ class _QKNormRope(torch.autograd.Function):
                                           dwq.data_ptr(), dwk.data_ptr(), T, Hq, Hk, D, stream_ptr()),
                 "vb200_qknorm_rope_bwd",
             )
-        return dq_in, dk_in, dwq.to(ctx.w_dtypes[0]), dwk.to(ctx.w_dtypes[1]), None, None, None
+        return dq_in, dk_in, dwq.to(ctx.w_dtypes[0]), dwk.to(ctx.w_dtypes[1]), None, None, None, None
 
 
-def qknorm_rope(q, k, q_norm_weight, k_norm_weight, cos, sin, eps: float):
-    """Per-head RMSNorm of q ``[T,Hq,D]`` / k ``[T,Hk,D]`` followed by RoPE, one HBM pass."""
-    return _QKNormRope.apply(q, k, q_norm_weight, k_norm_weight, cos, sin, eps)
+def qknorm_rope(q, k, q_norm_weight, k_norm_weight, cos, sin, eps: float, out=None):
+    """Per-head RMSNorm of q ``[T,Hq,D]`` / k ``[T,Hk,D]`` followed by RoPE, one HBM pass.
+    ``out=(q_out, k_out)`` writes the results into caller-provided buffers (e.g. the Ulysses send staging)."""
+    return _QKNormRope.apply(q, k, q_norm_weight, k_norm_weight, cos, sin, eps, out)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -114,11 +114,15 @@ class Qwen3Attention(nn.Module):
         k = self.k_proj(x).view(T, cfg.num_key_value_heads, D)
         v = self.v_proj(x).view(T, cfg.num_key_value_heads, D)
         # q_norm / k_norm + apply_rotary_pos_emb (:305-310) in one pass
-        q, k = F.qknorm_rope(q, k, self.q_norm.weight, self.k_norm.weight, cos, sin, cfg.rms_norm_eps)
+        out = None
         if sp_group is not None:
             from . import ulysses as U
 
             P = torch.distributed.get_world_size(sp_group)
+            if P <= cfg.num_key_value_heads:  # write q, k straight into the Ulysses send staging (copy-free exchange)
+                out = tuple(U.staging_views([tuple(q.shape), tuple(k.shape), tuple(v.shape)], q.dtype, sp_group)[:2])
+        q, k = F.qknorm_rope(q, k, self.q_norm.weight, self.k_norm.weight, cos, sin, cfg.rms_norm_eps, out=out)
+        if sp_group is not None:
             if P > cfg.num_key_value_heads:  # KV head replication (ops/kernels/attention/__init__.py:245-255)
                 k = torch.repeat_interleave(k, P // cfg.num_key_value_heads, dim=1)
                 v = torch.repeat_interleave(v, P // cfg.num_key_value_heads, dim=1)

@@ -90,6 +90,30 @@ def _stage_for(symm: SymmetricMemory) -> _Stage:
     return _stages[id(symm)]
 
 
+def staging_views(shapes: list[tuple[int, ...]], dtype: torch.dtype, group: dist.ProcessGroup | None = None,
+                  symm: SymmetricMemory | None = None) -> list[torch.Tensor]:
+    """Views into the persistent send-staging block that the next ``all_to_all_many`` of the same shapes will use.
+    A producer (e.g. the fused q/k-norm + RoPE kernel) can write its output there, which makes the exchange
+    copy-free for those tensors ("optional fusion of RoPE+qk-RMSNorm on the way out")."""
+    symm = symm if symm is not None else get_symmetric_memory(group)
+    stage = _stage_for(symm)
+    nbytes = [_numel(s) * dtype.itemsize for s in shapes]
+    sizes = [(n + 255) // 256 * 256 for n in nbytes]
+    buf = stage.get(len(shapes), sum(sizes))
+    views, off = [], 0
+    for shp, n, sz in zip(shapes, nbytes, sizes):
+        views.append(buf[off : off + n].view(dtype).view(*shp))
+        off += sz
+    return views
+
+
+def _numel(shape) -> int:
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
 def all_to_all_many(xs: list[torch.Tensor], scatter_dim: int, gather_dim: int, group: dist.ProcessGroup | None = None,
                     symm: SymmetricMemory | None = None, num_ctas: int = 32) -> list[torch.Tensor]:
     """Exchange up to 4 tensors (e.g. q, k, v) in ONE kernel launch."""
@@ -110,7 +134,9 @@ def all_to_all_many(xs: list[torch.Tensor], scatter_dim: int, gather_dim: int, g
             raise VB200Error("ulysses a2a runs on CUDA tensors only (no gloo/CPU fallback)")
         out_shape, d = a2a_plan(tuple(x.shape), scatter_dim, gather_dim, world, x.element_size())
         n = x.numel() * x.element_size()
-        buf[off : off + n].view(x.dtype).view(x.shape).copy_(x)  # stage (one local pass)
+        slot = buf[off : off + n].view(x.dtype).view(x.shape)
+        if x.data_ptr() != slot.data_ptr() or not x.is_contiguous():
+            slot.copy_(x)  # stage (one local pass) unless the producer already wrote into the staging view
         out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
         descs.append((off, d[0], d[1], out.data_ptr(), d[2], d[3], d[4], d[5]))
         outs.append(out)
