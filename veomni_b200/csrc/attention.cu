@@ -26,6 +26,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 struct AttnParams {
     const int* cu_seqlens;
     int num_seqs, Hq, Hk, total;
+    int tiles;  // 1-D grid = tiles x heads x num_seqs, ordered heaviest tile first (attention_tc.cu: tile_of_block)
     float scale;
     int causal;
     // forward
@@ -37,6 +38,15 @@ struct AttnParams {
     __nv_bfloat16 *dq, *dk, *dv;
     int64_t dq_stride_tok, dq_stride_head, dk_stride_tok, dk_stride_head, dv_stride_tok, dv_stride_head;
 };
+
+// linear block id -> (position in the heavy-to-light tile order, head, sequence); see attention_tc.cu
+__device__ __forceinline__ void tile_of_block(int heads, int nseq, int& order, int& head, int& seq) {
+    const int per = heads * nseq;
+    order = (int)blockIdx.x / per;
+    const int rem = (int)blockIdx.x - order * per;
+    seq = rem / heads;
+    head = rem - seq * heads;
+}
 
 __device__ __forceinline__ float quad_max(float v) {
     v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -87,9 +97,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * BN * HD * 2);  // barQ, fullK[2], fullV[2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int seq = blockIdx.z, h = blockIdx.y;
+    int order, h, seq;
+    tile_of_block(p.Hq, p.num_seqs, order, h, seq);
     const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
-    const int mblk = (int)gridDim.x - 1 - (int)blockIdx.x;  // heaviest (latest) row tiles first
+    const int mblk = p.tiles - 1 - order;  // heaviest (latest) row tiles first
     const int m0 = mblk * BM;
     if (m0 >= L) return;
     const int hk = h / (p.Hq / p.Hk);
@@ -255,9 +266,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint8_t* sV = sK + 2 * BN * HD * 2;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * BN * HD * 2);  // barQ, fullK[2], fullV[2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seq = blockIdx.z, h = blockIdx.y;
+    int order, h, seq;
+    tile_of_block(p.Hq, p.num_seqs, order, h, seq);
     const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
-    const int mblk = (int)gridDim.x - 1 - (int)blockIdx.x;
+    const int mblk = p.tiles - 1 - order;
     const int m0 = mblk * BM;
     if (m0 >= L) return;
     const int hk = h / (p.Hq / p.Hk);
@@ -368,9 +380,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     uint8_t* sdO = sQ + 2 * BMQ * HD * 2;        // 2 stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(sdO + 2 * BMQ * HD * 2);  // barKV, full[2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seq = blockIdx.z, hk = blockIdx.y;
+    int order, hk, seq;
+    tile_of_block(p.Hk, p.num_seqs, order, hk, seq);
     const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
-    const int n0 = blockIdx.x * BNK;
+    const int n0 = order * BNK;
     if (n0 >= L) return;
     const int G = p.Hq / p.Hk;
     const int i_start = p.causal ? n0 / BMQ : 0;
@@ -497,7 +510,8 @@ static int fwd_impl(const void* q, const void* k, const void* v, void* o, float*
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    dim3 grid((max_seqlen + 127) / 128, Hq, num_seqs);
+    p.tiles = (max_seqlen + 127) / 128;
+    dim3 grid(p.tiles * Hq * num_seqs);
     attn_fwd_kernel<HD><<<grid, 256, smem, stream>>>(tmQ, tmK, tmV, p);
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
@@ -536,10 +550,11 @@ static int bwd_impl(const void* q, const void* k, const void* v, const void* o, 
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
         attr = true;
     }
-    dim3 gq((max_seqlen + 127) / 128, Hq, num_seqs);
+    p.tiles = (max_seqlen + 127) / 128;
+    dim3 gq(p.tiles * Hq * num_seqs);
     attn_bwd_dq_kernel<HD><<<gq, 256, smem_dq, stream>>>(tmQ128, tmdO128, tmK64, tmV64, p);
     VB_HOST_CHECK_LAUNCH();
-    dim3 gk((max_seqlen + 127) / 128, Hk, num_seqs);
+    dim3 gk(p.tiles * Hk * num_seqs);
     attn_bwd_dkdv_kernel<HD><<<gk, 256, smem_kv, stream>>>(tmK128, tmV128, tmQ64, tmdO64, p);
     vb200_count_launch(3);
     VB_HOST_CHECK_LAUNCH();

@@ -19,6 +19,7 @@ namespace vb {
 struct AttnTcParams {
     const int* cu_seqlens;
     int Hq, Hk, total;
+    int tiles, nseq;  // 1-D grid = tiles x heads x nseq, heaviest tiles first (see tile_of_block)
     float scale;
     int causal;
     __nv_bfloat16* o;
@@ -27,6 +28,20 @@ struct AttnTcParams {
 };
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_D = 128;
+
+// Block order. With a causal mask the work of a tile grows (Q tiles) or shrinks (KV tiles) linearly with its
+// index, and the hardware hands CTAs to SMs in linear block order. A (tile, head, seq) 3-D grid runs one head's
+// tiles heavy-to-light and then starts the next head's heaviest tile late: list-scheduling that order on 148 SMs
+// costs 264 (fwd, dQ) and 376 (dK/dV) tile-units against an ideal 228 at T=4096, 32/8 heads. Ordering the 1-D grid
+// by tile first — every head's heaviest tile, then every head's second heaviest, ... (longest-processing-time
+// first) — gives 232 and 256. `order` = position in that list; returns the slot's (order, head, seq).
+__device__ __forceinline__ void tile_of_block(int heads, int nseq, int& order, int& head, int& seq) {
+    const int per = heads * nseq;
+    order = (int)blockIdx.x / per;
+    const int rem = (int)blockIdx.x - order * per;
+    seq = rem / heads;
+    head = rem - seq * heads;
+}
 constexpr int TC_TILE = TC_BM * TC_D * 2;  // 32 KB
 constexpr int TC_VSTAGES = 3;              // V is held until PV_j retires (one tile later than K): deeper ring
 constexpr float kLog2eTc = 1.4426950408889634f;
@@ -70,9 +85,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int seq = blockIdx.z, h = blockIdx.y;
+    int order, h, seq;
+    tile_of_block(p.Hq, p.nseq, order, h, seq);
     const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
-    const int mblk = (int)gridDim.x - 1 - (int)blockIdx.x;
+    const int mblk = p.tiles - 1 - order;  // causal: the last Q tile is the heaviest
     const int m0 = mblk * TC_BM;
     if (m0 >= L) return;
     const int hk = h / (p.Hq / p.Hk);
@@ -278,6 +294,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 struct AttnTcBwdParams {
     const int* cu_seqlens;
     int Hq, Hk, total;
+    int tiles, nseq;
     float scale;
     int causal;
     const float* lse;    // [Hq, total]
@@ -295,7 +312,7 @@ constexpr int TB_KV = 4;  // K/V smem ring depth of the dQ kernel: K_j is held f
 enum { Q_LOAD = 0, Q_KFULL = 1, Q_VFULL = 5, Q_KEMPTY = 9, Q_VEMPTY = 13, Q_SPFULL = 17, Q_SEMPTY = 19, Q_DSFULL = 21,
        Q_DSEMPTY = 23, Q_DONE = 25, Q_COUNT = 26 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const AttnTcBwdParams p) {
@@ -308,9 +325,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint64_t* bar = reinterpret_cast<uint64_t*>(sdS + 2 * TB_DS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + Q_COUNT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seq = blockIdx.z, h = blockIdx.y;
+    int order, h, seq;
+    tile_of_block(p.Hq, p.nseq, order, h, seq);
     const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
-    const int mblk = (int)gridDim.x - 1 - (int)blockIdx.x;
+    const int mblk = p.tiles - 1 - order;  // causal: the last Q tile is the heaviest
     const int m0 = mblk * TC_BM;
     if (m0 >= L) return;
     const int hk = h / (p.Hq / p.Hk);
@@ -320,7 +338,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < Q_COUNT; ++i) {
             const bool by_warps = (i >= Q_SEMPTY && i < Q_SEMPTY + 2) || (i >= Q_DSFULL && i < Q_DSFULL + 2);
-            mbar_init(&bar[i], by_warps ? 4 : 1);
+            mbar_init(&bar[i], by_warps ? 8 : 1);
         }
         mbar_fence_init();
     }
@@ -406,7 +424,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
         }
     } else {
+        // 8 softmax warps: warps w and w+4 share TMEM lane quadrant (w & 3) and split the tile's two 32-column chunks
         const int q = warp & 3;
+        const int cw = (warp - 2) >> 2;  // column chunk of this warp
         const int r = q * 32 + lane;
         const int m = m0 + r;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
@@ -426,8 +446,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const uint32_t ds_a = smem_u32(sdS + st * TB_DS);
             // tiles fully below the diagonal and inside the sequence need no per-element predicate
             const bool need_mask = (j * TB_N + TB_N > L) || (m0 + TC_BM > L) || (p.causal && j * TB_N + TB_N > m0);
-#pragma unroll 1
-            for (int c = 0; c < TB_N / 32; ++c) {
+            {
+                const int c = cw;
                 uint32_t sv[32], dv[32];
                 tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
@@ -470,7 +490,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_fence_after();
         __nv_bfloat16* row = p.dq + (int64_t)(s0 + m) * p.dq_st + (int64_t)h * p.dq_sh;
 #pragma unroll 1
-        for (int c = 0; c < TC_D / 32; ++c) {
+        for (int c = cw * 2; c < cw * 2 + 2; ++c) {
             uint32_t v[32];
             tmem_ld32(lane_base + 256 + c * 32, v);
             if (m < L) {
@@ -499,7 +519,7 @@ constexpr int TB_QS = 3;  // Q/dO smem ring depth of the dK/dV kernel
 enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = 4, K_STFULL = 7, K_STEMPTY = 9, K_PFULL = 11, K_PEMPTY = 13, K_DONE = 15,
        K_COUNT = 16 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                         const AttnTcBwdParams p) {
@@ -514,9 +534,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + K_COUNT);
     float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2 stages][lse2 x64 | delta x64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seq = blockIdx.z, hk = blockIdx.y;
+    int order, hk, seq;
+    tile_of_block(p.Hk, p.nseq, order, hk, seq);
     const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
-    const int n0 = blockIdx.x * TC_BM;
+    const int n0 = order * TC_BM;  // causal: the first KV tile is the heaviest
     if (n0 >= L) return;
     const int G = p.Hq / p.Hk;
     const int i_start = p.causal ? n0 / TB_N : 0;
@@ -526,7 +547,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     if (threadIdx.x == 0) {
         for (int i = 0; i < K_COUNT; ++i) {
             const bool by_warps = (i >= K_STEMPTY && i < K_STEMPTY + 2) || (i >= K_PFULL && i < K_PFULL + 2);
-            mbar_init(&bar[i], by_warps ? 4 : 1);
+            mbar_init(&bar[i], by_warps ? 8 : 1);
         }
         mbar_fence_init();
     }
@@ -614,31 +635,35 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             }
         }
     } else {
+        // 8 softmax warps: warps w and w+4 share TMEM lane quadrant (w & 3) and split the tile's two 32-column chunks
         const int q = warp & 3;
+        const int cw = (warp - 2) >> 2;
         const int r = q * 32 + lane;
+        const int tid = (warp - 2) * 32 + lane;  // 0..255 over the softmax warps
         const int n = n0 + r;  // kv index of this thread's row
+        // per-column statistics of the first job are fetched up front; each later job's are prefetched one job ahead
+        auto load_stat = [&](int jb) -> float {
+            if (jb >= jobs || tid >= 128) return 0.f;
+            const int hh = hk * G + jb / nq, qi = i_start + jb % nq;
+            const int mm = qi * TB_N + (tid & 63);
+            if (mm >= L) return 0.f;
+            if (tid < 64) {
+                const float l = p.lse[(int64_t)hh * p.total + s0 + mm];
+                return (l == -INFINITY) ? 0.f : l * kLog2eTc;
+            }
+            return p.delta[(int64_t)hh * p.total + s0 + mm];
+        };
+        float stat_next = load_stat(0);
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         const float sl2 = p.scale * kLog2eTc;
         for (int jb = 0; jb < jobs; ++jb) {
             const int st = jb & 1;
             const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
-            const int hh = hk * G + jb / nq, qi = i_start + jb % nq;
-            // per-column (q index) softmax statistics of this q tile: 64 lse + 64 delta values through smem
-            {
-                float* stat = sStat + st * 128;
-                const int mm = qi * TB_N + (r & 63);
-                float val = 0.f;
-                if (mm < L) {
-                    if (r < 64) {
-                        const float l = p.lse[(int64_t)hh * p.total + s0 + mm];
-                        val = (l == -INFINITY) ? 0.f : l * kLog2eTc;
-                    } else {
-                        val = p.delta[(int64_t)hh * p.total + s0 + mm];
-                    }
-                }
-                stat[r] = val;
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 softmax warps only
-            }
+            const int qi = i_start + jb % nq;
+            // per-column (q index) softmax statistics of this q tile: 64 lse2 + 64 delta values through smem
+            if (tid < 128) (sStat + st * 128)[tid] = stat_next;
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps only
+            stat_next = load_stat(jb + 1);
             const float* lse_s = sStat + st * 128;
             const float* dl_s = lse_s + 64;
             mbar_wait(&bar[K_STFULL + st], ph);
@@ -646,8 +671,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             mbar_wait(&bar[K_PEMPTY + st], ph ^ 1);
             const uint32_t pt_a = smem_u32(sPt + st * TB_DS), dst_a = smem_u32(sdSt + st * TB_DS);
             const bool need_mask = (qi * TB_N + TB_N > L) || (n0 + TC_BM > L) || (p.causal && n0 + TC_BM > qi * TB_N);
-#pragma unroll 1
-            for (int c = 0; c < TB_N / 32; ++c) {
+            {
+                const int c = cw;
                 uint32_t sv[32], dv[32];
                 tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
@@ -704,7 +729,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         __nv_bfloat16* vrow = p.dv + (int64_t)(s0 + n) * p.dv_st + (int64_t)hk * p.dv_sh;
         __nv_bfloat16* krow = p.dk + (int64_t)(s0 + n) * p.dk_st + (int64_t)hk * p.dk_sh;
 #pragma unroll 1
-        for (int c = 0; c < TC_D / 32; ++c) {
+        for (int c = cw * 2; c < cw * 2 + 2; ++c) {
             uint32_t v[32], kk[32];
             tmem_ld32(lane_base + 256 + c * 32, v);
             tmem_ld32(lane_base + 384 + c * 32, kk);
@@ -762,7 +787,9 @@ extern "C" int vb200_attn_varlen_fwd_tc(const void* q, const void* k, const void
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    dim3 grid((max_seqlen + TC_BM - 1) / TC_BM, q_heads, num_seqs);
+    p.tiles = (max_seqlen + TC_BM - 1) / TC_BM;
+    p.nseq = num_seqs;
+    dim3 grid(p.tiles * q_heads * num_seqs);
     attn_fwd_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
@@ -810,15 +837,17 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
         attr = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    dim3 gq((max_seqlen + TC_BM - 1) / TC_BM, q_heads, num_seqs);
+    p.tiles = (max_seqlen + TC_BM - 1) / TC_BM;
+    p.nseq = num_seqs;
+    dim3 gq(p.tiles * q_heads * num_seqs);
     if (only != 2) {
-        attn_bwd_dq_tc_kernel<<<gq, 192, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        attn_bwd_dq_tc_kernel<<<gq, 320, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         vb200_count_launch(1);
         VB_HOST_CHECK_LAUNCH();
     }
-    dim3 gk((max_seqlen + TC_BM - 1) / TC_BM, k_heads, num_seqs);
+    dim3 gk(p.tiles * k_heads * num_seqs);
     if (only != 1) {
-        attn_bwd_dkdv_tc_kernel<<<gk, 192, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+        attn_bwd_dkdv_tc_kernel<<<gk, 320, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
         vb200_count_launch(1);
     }
     VB_HOST_CHECK_LAUNCH();
