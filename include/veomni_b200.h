@@ -95,6 +95,28 @@ int vb200_swiglu_bwd(const void* dout, const void* gate, const void* up, void* d
                      int64_t rows, int64_t cols, int64_t in_stride, int64_t dout_stride,
                      int64_t dgrad_stride, void* stream);
 
+/* ---- softmax cross-entropy over the vocabulary ------------------------------------------
+ * Replaces the arithmetic of eager_cross_entropy -> transformers fixed_cross_entropy
+ * (veomni/ops/kernels/cross_entropy/eager.py:23-38) and of the liger fused-linear-cross-entropy
+ * element kernel (veomni/ops/kernels/cross_entropy/liger.py) as bound by ForCausalLMLoss
+ * (veomni/ops/kernels/cross_entropy/__init__.py:89-221).
+ *   logits  [rows, vocab], dtype 0 = bf16, 1 = f32, row stride in elements
+ *   labels  [rows] int64; rows with label == ignore_index contribute loss 0 and gradient 0
+ *   loss_rows[r] = logsumexp(x_r) - x_r[label_r]   (fp32, natural log; may be NULL)
+ *   lse[r]       = logsumexp(x_r): written when lse_given == 0 (may be NULL), read when lse_given != 0
+ *                  (backward-only call: the max/sum pass is skipped)
+ *   grad         = (softmax(x) - onehot(label)) * scale * (*scale_dev) * (*upstream), same dtype as
+ *                  logits; NULL = forward only; may alias logits (in place). scale_dev / upstream are
+ *                  optional device scalars (e.g. 1/valid-token-count and the incoming dLoss), so the
+ *                  mean reduction needs no host synchronisation.                            */
+int vb200_cross_entropy(const void* logits, int32_t dtype, int64_t rows, int64_t vocab, int64_t row_stride,
+                        const int64_t* labels, int64_t ignore_index, float* loss_rows, float* lse,
+                        int32_t lse_given, void* grad, int64_t grad_stride, float scale,
+                        const float* scale_dev, const float* upstream, void* stream);
+/* out2[0] = 1 / count(labels != ignore_index) (0 if none), out2[1] = that count; device scalars. */
+int vb200_count_valid_labels(const int64_t* labels, int64_t n, int64_t ignore_index, float* out2,
+                             void* stream);
+
 /* ---- packed (varlen) causal attention ---------------------------------------------------
  * Replaces flash_attn_varlen_func as called by flash_attention_forward
  * (veomni/ops/kernels/attention/__init__.py:304-320 through HF _flash_attention_forward's

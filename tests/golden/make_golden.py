@@ -34,6 +34,7 @@ sys.path.insert(0, "/root/reference")
 
 from oracle import attention as o_attn  # noqa: E402
 from oracle import comm as o_comm  # noqa: E402
+from oracle import loss as o_loss  # noqa: E402
 from oracle import moe as o_moe  # noqa: E402
 from oracle import ops as o_ops  # noqa: E402
 
@@ -348,9 +349,53 @@ def gen_qwen3_toy():
     }, HERE / "qwen3_toy.pt")
 
 
+# ----------------------------------------------------------------------------------------------
+def gen_loss():
+    """ForCausalLMLoss bound to the reference's eager cross-entropy, on CPU: logits path and hidden+weights path."""
+    from functools import partial
+
+    from veomni.ops.kernels.cross_entropy import ForCausalLMLoss
+    from veomni.ops.kernels.cross_entropy.eager import eager_cross_entropy
+
+    loss_fn = partial(ForCausalLMLoss, cross_entropy_fn=eager_cross_entropy)
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    T, H, V = 70, 48, 1003  # odd vocabulary: exercises the scalar head/tail of the vectorised kernel
+    labels = torch.randint(0, V, (1, T), generator=g)
+    labels[0, 5:9] = -100
+    labels[0, -3] = -100
+    for dtype, tag in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        for nib in (None, 50):
+            key = f"{tag}/{'mean' if nib is None else 'sum'}"
+            # (a) logits given
+            logits = (torch.randn(1, T, V, generator=g) * 2.0).to(dtype).requires_grad_(True)
+            loss, _, _ = loss_fn(logits=logits, labels=labels, vocab_size=V, num_items_in_batch=nib)
+            (gl,) = torch.autograd.grad(loss, logits)
+            sl = o_loss.shift_labels(labels).reshape(-1)
+            lo = o_loss.cross_entropy(logits.detach().reshape(-1, V), sl, nib)
+            eq(lo, loss.detach(), f"cross_entropy loss {key}", atol=1e-6, rtol=1e-6)
+            scale = 1.0 / float((sl != -100).sum()) if nib is None else 1.0 / nib
+            go = o_loss.cross_entropy_grad(logits.detach().reshape(-1, V), sl, scale).to(dtype)
+            eq(go, gl.reshape(-1, V), f"cross_entropy grad {key}", atol=1e-7 if dtype == torch.float32 else 1e-4, rtol=1e-5 if dtype == torch.float32 else 8e-3)
+            out[f"logits/{key}"] = {"logits": logits.detach(), "labels": labels, "num_items": nib, "loss": loss.detach(), "grad": gl}
+            # (b) hidden states + lm_head weight (eager: F.linear(...).float())
+            h = torch.randn(1, T, H, generator=g).to(dtype).requires_grad_(True)
+            w = (torch.randn(V, H, generator=g) * 0.2).to(dtype).requires_grad_(True)
+            loss, _, _ = loss_fn(labels=labels, vocab_size=V, num_items_in_batch=nib, hidden_states=h, weights=w)
+            gh, gw = torch.autograd.grad(loss, (h, w))
+            lo, dho, dwo = o_loss.fused_linear_cross_entropy(h.detach()[0], w.detach(), sl, nib, chunk_size=32)
+            tol = dict(atol=1e-6, rtol=1e-5) if dtype == torch.float32 else dict(atol=2e-3, rtol=2e-2)
+            eq(lo, loss.detach(), f"fused-linear loss {key}", atol=1e-5, rtol=1e-5)
+            eq(dho, gh[0], f"fused-linear d hidden {key}", **tol)
+            eq(dwo, gw, f"fused-linear d weight {key}", **tol)
+            out[f"linear/{key}"] = {"hidden": h.detach(), "weight": w.detach(), "labels": labels, "num_items": nib,
+                                    "loss": loss.detach(), "grad_hidden": gh, "grad_weight": gw}
+    torch.save(out, HERE / "loss.pt")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["ops", "moe", "multirank", "qwen3"]
+    which = sys.argv[1:] or ["ops", "moe", "multirank", "qwen3", "loss"]
     if "ops" in which:
         print("ops"); gen_ops()
     if "moe" in which:
@@ -359,4 +404,6 @@ if __name__ == "__main__":
         print("multirank"); gen_multirank()
     if "qwen3" in which:
         print("qwen3 toy"); gen_qwen3_toy()
+    if "loss" in which:
+        print("loss"); gen_loss()
     print("golden fixtures written to", HERE)

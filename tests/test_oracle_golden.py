@@ -123,3 +123,29 @@ def test_fsdp_collectives_match_reference(golden):
             assert torch.equal(shards[r].view(ref.shape), ref)
         ag = o_comm.fsdp_all_gather([c.reshape(-1) for c in full[name].chunk(world, dim=0)], torch.bfloat16)
         assert torch.equal(ag.view(full[name].shape), full[name].to(torch.bfloat16))
+
+
+def test_causal_lm_loss_matches_reference(golden):
+    """ForCausalLMLoss + eager_cross_entropy (logits path) and the chunked fused-linear restatement."""
+    from oracle import loss as o_loss
+
+    g = golden("loss.pt")
+    for key, f in g.items():
+        kind, tag, red = key.split("/")
+        sl = o_loss.shift_labels(f["labels"]).reshape(-1)
+        fp32 = tag == "fp32"
+        if kind == "logits":
+            V = f["logits"].shape[-1]
+            x = f["logits"].reshape(-1, V)
+            loss = o_loss.cross_entropy(x, sl, f["num_items"])
+            torch.testing.assert_close(loss, f["loss"], atol=1e-6, rtol=1e-6, msg=key)
+            scale = 1.0 / float((sl != -100).sum()) if f["num_items"] is None else 1.0 / f["num_items"]
+            grad = o_loss.cross_entropy_grad(x, sl, scale).to(x.dtype)
+            torch.testing.assert_close(grad, f["grad"].reshape(-1, V), atol=1e-7 if fp32 else 1e-4, rtol=1e-5 if fp32 else 8e-3, msg=key)
+            assert torch.all(grad[sl == -100] == 0)
+        else:
+            loss, dh, dw = o_loss.fused_linear_cross_entropy(f["hidden"][0], f["weight"], sl, f["num_items"], chunk_size=32)
+            tol = dict(atol=1e-6, rtol=1e-5) if fp32 else dict(atol=2e-3, rtol=2e-2)
+            torch.testing.assert_close(loss, f["loss"], atol=1e-5, rtol=1e-5, msg=key)
+            torch.testing.assert_close(dh, f["grad_hidden"][0], msg=key, **tol)
+            torch.testing.assert_close(dw, f["grad_weight"], msg=key, **tol)

@@ -9,7 +9,8 @@ def test_eager_resolves_to_none_and_unknown_raises_keyerror():
     with pytest.raises(KeyError):
         R.KERNEL_REGISTRY.resolve("rms_norm", "standard", "does_not_exist")
     assert "b200" in R.KERNEL_REGISTRY.list_available("rms_norm", "standard")
-    for op, var in (("rotary_pos_emb", "full"), ("swiglu_mlp", "standard"), ("moe_experts", "standard")):
+    for op, var in (("rotary_pos_emb", "full"), ("swiglu_mlp", "standard"), ("moe_experts", "standard"),
+                    ("cross_entropy_loss", "causal"), ("cross_entropy_loss", "seq_cls")):
         assert "b200" in R.KERNEL_REGISTRY.list_available(op, var)
 
 
@@ -55,8 +56,16 @@ def test_register_into_the_real_reference_when_present():
         from transformers.modeling_utils import ALL_ATTENTION_FUNCTIONS
         from veomni.ops.kernel_registry import KERNEL_REGISTRY as REF
 
-        for op, var in (("rms_norm", "standard"), ("rotary_pos_emb", "full"), ("swiglu_mlp", "standard"), ("moe_experts", "standard")):
+        for op, var in (("rms_norm", "standard"), ("rotary_pos_emb", "full"), ("swiglu_mlp", "standard"), ("moe_experts", "standard"),
+                        ("cross_entropy_loss", "causal"), ("cross_entropy_loss", "seq_cls")):
             assert "b200" in REF.list_available(op, var)
+        # the causal-LM loss factory binds OUR kernel into THEIR wrapper (label shift + SP reduce stay theirs)
+        import veomni.ops.kernels.cross_entropy as ref_ce
+        from veomni_b200.cross_entropy import b200_cross_entropy
+
+        spec = [s for s in R._specs() if s.op_name == "cross_entropy_loss" and s.variant == "causal"][0]
+        bound = spec.factory()
+        assert bound.func is ref_ce.ForCausalLMLoss and bound.keywords["cross_entropy_fn"] is b200_cross_entropy
         assert R.ATTN_NAME in ALL_ATTENTION_FUNCTIONS.valid_keys()
         import veomni.distributed.sequence_parallel.ulysses as u
 

@@ -149,7 +149,38 @@ def bench_swiglu(dev, iters):
     report("swiglu_bwd[4096x12288]", time_fn(bwd, sets, iters), nbytes=5 * T * I * 2)
 
 
-BENCHES = {"rmsnorm": bench_rmsnorm, "rope": bench_rope, "swiglu": bench_swiglu}
+def bench_loss(dev, iters):
+    """One 1024-row chunk of the 151936-entry vocabulary, bf16, gradient written in place: read + write once."""
+    rows, V = 1024, 151936
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    labels = torch.randint(0, V, (rows,), device=dev)
+    sets = [(torch.randn(rows, V, device=dev, dtype=BF), torch.empty(rows, device=dev, dtype=torch.float32)) for _ in range(2)]
+
+    def fused(x, lr):  # forward statistics + in-place gradient (the fused-linear path's kernel)
+        lib.vb200_cross_entropy(x.data_ptr(), 0, rows, V, V, labels.data_ptr(), -100, lr.data_ptr(), None, 0, x.data_ptr(), V,
+                                1.0 / rows, None, None, st)
+
+    report("cross_entropy_fwd+grad_inplace[1024x151936 bf16]", time_fn(fused, sets, iters), nbytes=2 * rows * V * 2)
+
+    def fwd(x, lr):  # loss only
+        lib.vb200_cross_entropy(x.data_ptr(), 0, rows, V, V, labels.data_ptr(), -100, lr.data_ptr(), None, 0, None, 0,
+                                1.0, None, None, st)
+
+    report("cross_entropy_fwd[1024x151936 bf16]", time_fn(fwd, sets, iters), nbytes=rows * V * 2)
+    x32 = torch.randn(rows, V, device=dev, dtype=torch.float32)
+    g32 = torch.empty_like(x32)
+    lr = torch.empty(rows, device=dev, dtype=torch.float32)
+
+    def lib_ce():
+        xx = x32.detach().requires_grad_(True)
+        torch.nn.functional.cross_entropy(xx, labels).backward()
+
+    report("(lib) torch cross_entropy fwd+bwd[1024x151936 fp32]", time_fn(lambda: lib_ce(), [()], iters))
+    del g32, lr
+
+
+BENCHES = {"rmsnorm": bench_rmsnorm, "rope": bench_rope, "swiglu": bench_swiglu, "loss": bench_loss}
 
 
 def main():

@@ -112,7 +112,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(&bar[B_Q], TC_TILE);
             tma_load_3d(sQ, &tmQ, 0, h, s0 + m0, &bar[B_Q]);
             tma_load_3d(sQ + TC_BM * 128, &tmQ, 64, h, s0 + m0, &bar[B_Q]);
@@ -144,13 +144,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(&bar[B_SEMPTY + st], ph ^ 1);
                 mbar_wait(&bar[B_KFULL + st], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t k_addr = smem_u32(sK + st * TC_TILE);
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16(tmem + st * TC_BN, umma_desc(q_addr + off, 16, 1024), umma_desc(k_addr + off, 16, 1024),
-                                 idesc_qk, k ? 1u : 0u);
+                        umma_f16_bo(tmem + st * TC_BN, q_addr >> 4, off, 16, 1024, k_addr >> 4, off, 16, 1024,
+                                    idesc_qk, k ? 1u : 0u);
                     }
                     umma_commit(&bar[B_KEMPTY + st]);
                     umma_commit(&bar[B_SFULL + st]);
@@ -163,13 +163,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(&bar[B_VFULL + vs], vph);
                 mbar_wait(&bar[B_PFULL], (uint32_t)i & 1u);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t v_addr = smem_u32(sV + vs * TC_TILE);
 #pragma unroll
                     for (int k = 0; k < TC_BN / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16(tmem + 256, umma_desc(p_addr + a_off, 16, 1024),
-                                 umma_desc(v_addr + k * 16 * 128, TC_BN * 128, 1024), idesc_pv, (i | k) ? 1u : 0u);
+                        umma_f16_bo(tmem + 256, p_addr >> 4, a_off, 16, 1024, v_addr >> 4, k * 16 * 128, TC_BN * 128, 1024,
+                                    idesc_pv, (i | k) ? 1u : 0u);
                     }
                     umma_commit(&bar[B_VEMPTY + vs]);
                     umma_commit(&bar[B_PVDONE]);
@@ -350,7 +350,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     // TMEM columns: S[2] 0/64, dP[2] 128/192, dQ 256..383
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(&bar[Q_LOAD], 2 * TC_TILE);
             for (int hf = 0; hf < 2; ++hf) {
                 tma_load_3d(sQ + hf * TC_BM * 128, &tmQ, hf * 64, h, s0 + m0, &bar[Q_LOAD]);
@@ -384,21 +384,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 mbar_wait(&bar[Q_KFULL + ks], kph);
                 mbar_wait(&bar[Q_VFULL + ks], kph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t k_addr = smem_u32(sK + ks * TB_SMALL), v_addr = smem_u32(sV + ks * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
                         const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16(tmem + st * TB_N, umma_desc(q_addr + a_off, 16, 1024), umma_desc(k_addr + b_off, 16, 1024),
-                                 idesc_nt, k ? 1u : 0u);
+                        umma_f16_bo(tmem + st * TB_N, q_addr >> 4, a_off, 16, 1024, k_addr >> 4, b_off, 16, 1024,
+                                    idesc_nt, k ? 1u : 0u);
                     }
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
                         const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16(tmem + 128 + st * TB_N, umma_desc(do_addr + a_off, 16, 1024), umma_desc(v_addr + b_off, 16, 1024),
-                                 idesc_nt, k ? 1u : 0u);
+                        umma_f16_bo(tmem + 128 + st * TB_N, do_addr >> 4, a_off, 16, 1024, v_addr >> 4, b_off, 16, 1024,
+                                    idesc_nt, k ? 1u : 0u);
                     }
                     umma_commit(&bar[Q_VEMPTY + ks]);
                     umma_commit(&bar[Q_SPFULL + st]);
@@ -410,12 +410,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
                 mbar_wait(&bar[Q_DSFULL + st], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t ds_addr = smem_u32(sdS + st * TB_DS), k_addr = smem_u32(sK + ks * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TB_N / 16; ++k)
-                        umma_f16(tmem + 256, umma_desc(ds_addr + k * 32, 16, 1024),
-                                 umma_desc(k_addr + k * 16 * 128, TB_N * 128, 1024), idesc_dq, (i | k) ? 1u : 0u);
+                        umma_f16_bo(tmem + 256, ds_addr >> 4, k * 32, 16, 1024, k_addr >> 4, k * 16 * 128, TB_N * 128, 1024,
+                                    idesc_dq, (i | k) ? 1u : 0u);
                     umma_commit(&bar[Q_KEMPTY + ks]);
                     umma_commit(&bar[Q_DSEMPTY + st]);
                     if (i == n_tiles - 1) umma_commit(&bar[Q_DONE]);
@@ -559,7 +559,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     // TMEM columns: S^T[2] 0/64, dP^T[2] 128/192, dV 256..383, dK 384..511
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_expect_tx(&bar[K_LOAD], 2 * TC_TILE);
             for (int hf = 0; hf < 2; ++hf) {
                 tma_load_3d(sK + hf * TC_BM * 128, &tmK, hf * 64, hk, s0 + n0, &bar[K_LOAD]);
@@ -591,21 +591,21 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 mbar_wait(&bar[K_STEMPTY + st], ph ^ 1);
                 mbar_wait(&bar[K_QFULL + qs], qph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t q_addr = smem_u32(sQ + qs * TB_SMALL), do_addr = smem_u32(sdO + qs * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
                         const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16(tmem + st * TB_N, umma_desc(k_addr + a_off, 16, 1024), umma_desc(q_addr + b_off, 16, 1024),
-                                 idesc_nt, k ? 1u : 0u);
+                        umma_f16_bo(tmem + st * TB_N, k_addr >> 4, a_off, 16, 1024, q_addr >> 4, b_off, 16, 1024,
+                                    idesc_nt, k ? 1u : 0u);
                     }
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
                         const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16(tmem + 128 + st * TB_N, umma_desc(v_addr + a_off, 16, 1024), umma_desc(do_addr + b_off, 16, 1024),
-                                 idesc_nt, k ? 1u : 0u);
+                        umma_f16_bo(tmem + 128 + st * TB_N, v_addr >> 4, a_off, 16, 1024, do_addr >> 4, b_off, 16, 1024,
+                                    idesc_nt, k ? 1u : 0u);
                     }
                     umma_commit(&bar[K_STFULL + st]);
                 }
@@ -616,17 +616,17 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
                 mbar_wait(&bar[K_PFULL + st], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t pt_addr = smem_u32(sPt + st * TB_DS), dst_addr = smem_u32(sdSt + st * TB_DS);
                     const uint32_t q_addr = smem_u32(sQ + qs * TB_SMALL), do_addr = smem_u32(sdO + qs * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TB_N / 16; ++k)
-                        umma_f16(tmem + 256, umma_desc(pt_addr + k * 32, 16, 1024),
-                                 umma_desc(do_addr + k * 16 * 128, TB_N * 128, 1024), idesc_acc, (i | k) ? 1u : 0u);
+                        umma_f16_bo(tmem + 256, pt_addr >> 4, k * 32, 16, 1024, do_addr >> 4, k * 16 * 128, TB_N * 128, 1024,
+                                    idesc_acc, (i | k) ? 1u : 0u);
 #pragma unroll
                     for (int k = 0; k < TB_N / 16; ++k)
-                        umma_f16(tmem + 384, umma_desc(dst_addr + k * 32, 16, 1024),
-                                 umma_desc(q_addr + k * 16 * 128, TB_N * 128, 1024), idesc_acc, (i | k) ? 1u : 0u);
+                        umma_f16_bo(tmem + 384, dst_addr >> 4, k * 32, 16, 1024, q_addr >> 4, k * 16 * 128, TB_N * 128, 1024,
+                                    idesc_acc, (i | k) ? 1u : 0u);
                     umma_commit(&bar[K_QEMPTY + qs]);
                     umma_commit(&bar[K_PEMPTY + st]);
                     if (i == jobs - 1) umma_commit(&bar[K_DONE]);

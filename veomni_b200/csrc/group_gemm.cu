@@ -120,7 +120,7 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int s = 0;
             uint32_t ph = 0;
             TileInfo ti;
@@ -180,16 +180,15 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                     __syncwarp();
                 }
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
 #pragma unroll
                     for (int k = 0; k < GG_BK / 16; ++k) {
-                        uint64_t ad, bd;
-                        if (MODE == GG_TN) ad = umma_desc(a_addr + k * 16 * 128, GG_BK * 128, 1024);  // MN-major
-                        else ad = umma_desc(a_addr + k * 32, 16, 1024);                               // K-major
-                        if (MODE == GG_NT) bd = umma_desc(b_addr + k * 32, 16, 1024);
-                        else bd = umma_desc(b_addr + k * 16 * 128, GG_BK * 128, 1024);
-                        umma_f16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+                        // A: MN-major for TN (wgrad), else K-major; B: K-major for NT (fwd), else MN-major
+                        const uint32_t a_off = MODE == GG_TN ? k * 16 * 128 : k * 32, a_lbo = MODE == GG_TN ? GG_BK * 128 : 16;
+                        const uint32_t b_off = MODE == GG_NT ? k * 32 : k * 16 * 128, b_lbo = MODE == GG_NT ? 16 : GG_BK * 128;
+                        umma_f16_bo(tmem_d, a_addr >> 4, a_off, a_lbo, 1024, b_addr >> 4, b_off, b_lbo, 1024, idesc,
+                                    (kb | k) ? 1u : 0u);
                     }
                     umma_commit(&empty[s]);
                     if (kb == kblocks - 1) umma_commit(&tfull[acc]);

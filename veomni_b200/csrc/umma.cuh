@@ -17,11 +17,37 @@ __device__ __forceinline__ constexpr uint32_t umma_idesc(int a_mn_major, int b_m
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// True in exactly one lane of a converged warp. nvcc recognises the elect.sync idiom and emits the uniform-datapath
+// instructions (UTCHMMA / UTCBAR / UTMALDG) of the guarded region directly; under `if (lane == 0)` it wraps every one
+// of them in an ELECT / PLOP3 / BRA.U.ANY "waterfall" loop, which made the single MMA-issuing warp — not the tensor
+// pipe — the limiter of the attention backward kernels (ncu: ~600 SASS instructions per 20 MMAs).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same MMA with the descriptors given as (smem address >> 4) + byte offset: with the offset, LBO and SBO compile-time
+// constants (unrolled k loops) each descriptor costs one uniform add instead of a shift / mask / or chain.
+// Valid while the 14-bit start-address field cannot carry, i.e. for any shared-memory address (< 256 KB).
+__device__ __forceinline__ void umma_f16_bo(uint32_t tmem_d, uint32_t a16, uint32_t a_off, uint32_t a_lbo, uint32_t a_sbo,
+                                            uint32_t b16, uint32_t b_off, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc,
+                                            uint32_t accumulate) {
+    const uint32_t a_lo = a16 + ((a_off >> 4) + (((a_lbo >> 4) & 0x3FFFu) << 16));
+    const uint32_t b_lo = b16 + ((b_off >> 4) + (((b_lbo >> 4) & 0x3FFFu) << 16));
+    const uint32_t a_hi = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t b_hi = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

@@ -27,6 +27,7 @@ from torch.utils.checkpoint import checkpoint
 
 from . import functional as F
 from .attention import flash_attn_varlen
+from .cross_entropy import b200_cross_entropy
 
 
 @dataclass
@@ -172,6 +173,7 @@ class Qwen3ForCausalLM(nn.Module):
         if cfg.tie_word_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
         self.gradient_checkpointing = False
+        self.loss_impl = "fused"  # "fused": lm_head folded into the loss kernel's chunk loop; "logits": eager form
         self.keep_attention_in_checkpoint = True  # keep (o, lse) resident instead of recomputing attention
         self._fwd_counter = 0
         self.sp_group = None
@@ -216,14 +218,19 @@ class Qwen3ForCausalLM(nn.Module):
             else:
                 h = layer(h, cos, sin, cu_seqlens, max_seqlen, self.sp_group)
         h = self.model.norm(h)
-        logits = self.lm_head(h)
         if labels is None and shift_labels is None:
-            return logits
-        # ForCausalLMLoss (cross_entropy/__init__.py:180-221): fp32 logits, shift unless already shifted (SP)
+            return self.lm_head(h)
+        # ForCausalLMLoss (cross_entropy/__init__.py:180-221): shift unless already shifted (SP), then the bound
+        # cross_entropy_fn. "fused" hands hidden states + lm_head weight to the kernel (the reference's liger path);
+        # "logits" materialises bf16 logits and upcasts them like the reference's eager path.
         if shift_labels is None:
             shift_labels = Fnn.pad(labels, (0, 1), value=-100)[..., 1:].contiguous()
-        loss = Fnn.cross_entropy(logits.float().view(-1, self.config.vocab_size), shift_labels.reshape(-1),
-                                 ignore_index=-100)
+        if self.loss_impl == "fused":
+            loss, _ = b200_cross_entropy(None, shift_labels, self.config.vocab_size, hidden_states=h,
+                                         weights=self.lm_head.weight)
+        else:
+            loss, _ = b200_cross_entropy(self.lm_head(h).float().view(-1, self.config.vocab_size), shift_labels,
+                                         self.config.vocab_size)
         return loss
 
 

@@ -153,7 +153,33 @@ def _specs() -> list[KernelSpec]:
 
         return moe_experts_forward
 
+    def f_ce_causal():
+        # bound to the reference's own outer wrapper when VeOmni is installed (label shift + SP reduction live there),
+        # else to the mirror in .cross_entropy
+        from functools import partial
+
+        from .cross_entropy import ForCausalLMLoss as own, b200_cross_entropy
+
+        try:
+            from veomni.ops.kernels.cross_entropy import ForCausalLMLoss as ref_wrapper
+        except ImportError:
+            ref_wrapper = own
+        return partial(ref_wrapper, cross_entropy_fn=b200_cross_entropy)
+
+    def f_ce_seq_cls():
+        from functools import partial
+
+        from .cross_entropy import b200_cross_entropy
+
+        from veomni.ops.kernels.cross_entropy import ForSequenceClassificationLoss  # only exists inside VeOmni
+
+        return partial(ForSequenceClassificationLoss, cross_entropy_fn=b200_cross_entropy)
+
     return [
+        KernelSpec(IMPL_NAME, "cross_entropy_loss", "causal", f_ce_causal, _B200,
+                   "sm_100a fused linear + cross-entropy (chunked lm_head on cuBLAS, in-place gradient kernel)"),
+        KernelSpec(IMPL_NAME, "cross_entropy_loss", "seq_cls", f_ce_seq_cls, _B200,
+                   "sm_100a cross-entropy for sequence-classification heads"),
         KernelSpec(IMPL_NAME, "rms_norm", "standard", f_rms, _B200, "sm_100a RMSNorm (bulk-async staged rows)"),
         KernelSpec(IMPL_NAME, "rotary_pos_emb", "full", f_rope, _B200, "sm_100a RoPE"),
         KernelSpec(IMPL_NAME, "swiglu_mlp", "standard", f_swiglu, _B200, "sm_100a SiLU*up between cuBLAS GEMMs"),
