@@ -205,6 +205,17 @@ def run_b200(args) -> None:
     torch.cuda.synchronize()
     prof_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in prof.items()}
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
+    if args.torch_profile:  # debugging aid, outside every timed region: per-kernel device time of one step on rank 0
+        from torch.profiler import ProfilerActivity, profile
+
+        dist.barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as tp:
+            step(resident[0])
+            torch.cuda.synchronize()
+        if rank == 0:
+            with open(args.torch_profile, "w") as fh:
+                fh.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+        dist.barrier()
     clocks = sampler.stop() if rank == 0 else {}
     mem_gb = torch.cuda.max_memory_allocated() / 2**30
 
@@ -267,6 +278,7 @@ def main():
     ap.add_argument("--nccl-comm", action="store_true", help="debug: PyTorch's default NCCL FSDP2 collectives")
     ap.add_argument("--comm-ctas", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-profile", default="", help="debug: write a torch.profiler kernel table of one extra step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -105,7 +105,7 @@ def test_full_vocab_chunk_properties(cuda_dev):
 
 
 def test_cpu_tensors_are_rejected():
-    from veomni_b200 import VB200Error
+    from veomni_b200._lib import VB200Error
     from veomni_b200.cross_entropy import b200_cross_entropy
 
     with pytest.raises(VB200Error):

@@ -452,6 +452,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
                 tmem_wait_ld();
+                // S/dP[st] are in registers: release the TMEM buffer now so the MMA warp can run S/dP of tile j+2
+                // while this tile's exponentials are still being computed
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar[Q_SEMPTY + st]);
                 uint32_t pk[16];
                 if (need_mask) {
 #pragma unroll
@@ -481,10 +486,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             tc_fence_before();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bar[Q_SEMPTY + st]);
-                mbar_arrive(&bar[Q_DSFULL + st]);
-            }
+            if (lane == 0) mbar_arrive(&bar[Q_DSFULL + st]);
         }
         mbar_wait(&bar[Q_DONE], 0);
         tc_fence_after();
@@ -677,6 +679,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
                 tmem_wait_ld();
+                tc_fence_before();  // early release of S^T/dP^T[st] (see the dQ kernel)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar[K_STEMPTY + st]);
                 uint32_t pk[16], dk[16];
                 if (need_mask) {
 #pragma unroll
@@ -719,10 +724,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             tc_fence_before();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bar[K_STEMPTY + st]);
-                mbar_arrive(&bar[K_PFULL + st]);
-            }
+            if (lane == 0) mbar_arrive(&bar[K_PFULL + st]);
         }
         mbar_wait(&bar[K_DONE], 0);
         tc_fence_after();
