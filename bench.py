@@ -130,6 +130,7 @@ def run_b200(args) -> None:
 
     from veomni_b200 import _lib
     from veomni_b200 import attention as vattn
+    from veomni_b200.clip_grad_norm import clip_grad_norm
     from veomni_b200.host_qwen3 import Qwen3Config, Qwen3ForCausalLM, flops_per_token
     from veomni_b200.parallelize import build_parallelize_model
 
@@ -164,7 +165,7 @@ def run_b200(args) -> None:
         ids, labels, pos = batch
         loss = model(ids, pos, cu, SEQ_LEN, labels=labels)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        clip_grad_norm(model, 1.0)  # veomni_clip_grad_norm semantics, multi-tensor kernels
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -205,6 +206,24 @@ def run_b200(args) -> None:
     torch.cuda.synchronize()
     prof_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in prof.items()}
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
+    mem_gb = torch.cuda.max_memory_allocated() / 2**30
+    # The same step with every activation kept instead of recomputed (180 GB of HBM3e hold them at this size): reported
+    # next to the headline, which keeps the reference's default of per-layer gradient checkpointing.
+    no_rc = None
+    if not args.skip_no_recompute:
+        inner = getattr(model, "module", model)
+        prev = inner.gradient_checkpointing
+        inner.gradient_checkpointing = False
+        try:
+            torch.cuda.reset_peak_memory_stats()
+            for i in range(2):
+                step(resident[i % nbuf])
+            ms_nr, _ = timed(args.steps, e2e=False)
+            no_rc = {"value": round(SEQ_LEN * world / (ms_nr / 1e3), 1), "unit": "tokens/s", "ms_per_step": round(ms_nr, 2),
+                     "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1)}
+        except torch.OutOfMemoryError:
+            no_rc = {"value": None, "note": "out of memory without recomputation"}
+        inner.gradient_checkpointing = prev
     if args.torch_profile:  # debugging aid, outside every timed region: per-kernel device time of one step on rank 0
         from torch.profiler import ProfilerActivity, profile
 
@@ -217,7 +236,6 @@ def run_b200(args) -> None:
                 fh.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else {}
-    mem_gb = torch.cuda.max_memory_allocated() / 2**30
 
     if rank == 0:
         peaks = _peaks()
@@ -261,6 +279,8 @@ def run_b200(args) -> None:
                          "algorithmic_flops_per_launch": attn_flops},
             "clocks": clocks, "loss": round(loss_dev, 4), "loss_e2e": round(loss_e2e, 4), "max_mem_gb": round(mem_gb, 1),
         }
+        if no_rc is not None:
+            out["no_recompute"] = no_rc
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(sample_tokens=256, iters=1, threads=None)
         print(json.dumps(out), flush=True)
@@ -278,6 +298,7 @@ def main():
     ap.add_argument("--nccl-comm", action="store_true", help="debug: PyTorch's default NCCL FSDP2 collectives")
     ap.add_argument("--comm-ctas", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-no-recompute", action="store_true", help="skip the extra no-recomputation measurement")
     ap.add_argument("--torch-profile", default="", help="debug: write a torch.profiler kernel table of one extra step")
     args = ap.parse_args()
     if args.impl == "reference":

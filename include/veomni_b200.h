@@ -95,6 +95,23 @@ int vb200_swiglu_bwd(const void* dout, const void* gate, const void* up, void* d
                      int64_t rows, int64_t cols, int64_t in_stride, int64_t dout_stride,
                      int64_t dgrad_stride, void* stream);
 
+/* ---- gradient clipping: multi-tensor L2 norm and in-place scale ---------------------------
+ * Replaces the two passes of torch.nn.utils.clip_grad_norm_ under veomni_clip_grad_norm
+ * (veomni/distributed/clip_grad_norm.py:7-20 -> fsdp2/clip_grad_norm.py:21-51 dense,
+ * :73-153 expert groups): _foreach_norm over the local gradient shards and _foreach_mul_ by the
+ * clip coefficient.  ptrs_dev / numels_dev: device arrays of n entries (an entry is a whole
+ * tensor or a piece of one; keep entries <= 2^20 elements for balance); dtype 0 = bf16, 1 = f32.
+ *   vb200_multi_sumsq : total[0] = sum over entries of sum(x^2)  (fp32, fixed reduction order);
+ *                       per_entry (optional) [n] the per-entry sums; partials: workspace of
+ *                       vb200_multi_sumsq_partials(n) floats.
+ *   vb200_multi_scale : x *= *coef_dev for every entry; returns without touching memory when
+ *                       *coef_dev == 1 (no clipping needed).                                  */
+int64_t vb200_multi_sumsq_partials(int32_t n_entries);
+int vb200_multi_sumsq(const void* const* ptrs_dev, const int64_t* numels_dev, int32_t n_entries, int32_t dtype,
+                      float* partials, float* total, float* per_entry, void* stream);
+int vb200_multi_scale(void* const* ptrs_dev, const int64_t* numels_dev, int32_t n_entries, int32_t dtype,
+                      const float* coef_dev, void* stream);
+
 /* ---- softmax cross-entropy over the vocabulary ------------------------------------------
  * Replaces the arithmetic of eager_cross_entropy -> transformers fixed_cross_entropy
  * (veomni/ops/kernels/cross_entropy/eager.py:23-38) and of the liger fused-linear-cross-entropy
@@ -185,6 +202,20 @@ int vb200_allgather(void* comm, int32_t channel, int64_t region_offset, int64_t 
  * region_offset; out[i] = scale * sum_{p=0..N-1} chunk_rank(p)[i], summed in rank order.      */
 int vb200_reduce_scatter_f32(void* comm, int32_t channel, int64_t region_offset, int64_t chunk_elems,
                              float scale, float* out, int32_t num_ctas, void* stream);
+/* Same reduce-scatter with bf16 inputs (N chunks of chunk_elems bf16 at region_offset), fp32 accumulation
+ * in rank order and fp32 output: bit-identical to vb200_reduce_scatter_f32 on the fp32 copies of the same
+ * gradients (bf16 -> fp32 is exact), at half the NVLink bytes.                                       */
+int vb200_reduce_scatter_bf16(void* comm, int32_t channel, int64_t region_offset, int64_t chunk_elems,
+                              float scale, float* out, int32_t num_ctas, void* stream);
+/* Reduce-scatter copy-in, replaces foreach_reduce_scatter_copy_in -> torch._chunk_cat
+ * (torch/distributed/fsdp/_fully_shard/_fsdp_collectives.py:667-675) for bf16 gradients WITHOUT the
+ * conversion to the reduce dtype: out[r, off_p : off_p + chunk_p] = chunk r of parameter p
+ * (dim-0 zero-padded to a multiple of world), bf16.  desc: host array of n x {src pointer, numel,
+ * chunk elements, row offset}; src_dtype 0 = bf16, 1 = f32 (rounded to bf16).  With world = 1 and
+ * f32 sources it is also the all-gather copy-in (all_gather_copy_in_cuda, :175-188): the fp32 master
+ * shards cast into the bf16 all-gather input in one pass.                                            */
+int vb200_fsdp_pack_bf16(const int64_t* desc, int32_t n, int32_t world, int64_t row_elems, void* out,
+                         int32_t src_dtype, void* stream);
 /* Strided chunk exchange, replaces dist.all_to_all_single + the reshape/cat copies of
  * _all_to_all_single (veomni/distributed/sequence_parallel/ulysses.py:86-122).
  * desc: n_desc x 8 int64 = {src_off, src_rank_stride, src_row_stride, dst pointer,

@@ -62,6 +62,28 @@ def test_reduce_scatter(symm, rank, world, dev):
     symm.check()
 
 
+def test_reduce_scatter_bf16(symm, rank, world, dev):
+    """bf16-pull reduce-scatter == fp32 reduce-scatter of the fp32 copies (bit-exact) == the fixed-order oracle."""
+    for chunk in (1, 7, 1024, 4099, 1 << 18):
+        g = torch.Generator(device="cpu").manual_seed(91 * rank + chunk)
+        xb = torch.randn(chunk * world, generator=g).to(torch.bfloat16).to(dev)
+        # bf16 gradients packed into the first half of an fp32-sized buffer, as the patched copy-in leaves them
+        buf = symm.empty((chunk * world,), torch.float32, arena="fsdp_rs")
+        buf.view(torch.bfloat16)[: chunk * world].copy_(xb)
+        out = torch.empty(chunk, dtype=torch.float32, device=dev)
+        symm.reduce_scatter_bf16(buf, chunk, out, 1.0 / world, 1)
+        inp = symm.empty((chunk * world,), torch.float32, arena="fsdp_rs")
+        inp.copy_(xb.float())
+        out32 = torch.empty(chunk, dtype=torch.float32, device=dev)
+        symm.reduce_scatter_f32(inp, out32, 1.0 / world, 1)
+        xs = gather_all(xb.float())
+        ref = o_comm.fsdp_reduce_scatter([t.cpu() for t in xs], torch.float32, None)[rank] * (1.0 / world)
+        torch.cuda.synchronize()
+        assert torch.equal(out, out32), f"bf16-pull != fp32 reduce-scatter, chunk={chunk}"
+        assert torch.equal(out.cpu(), ref), f"bf16-pull reduce_scatter vs oracle, chunk={chunk}"
+    symm.check()
+
+
 def test_ulysses(rank, world, dev):
     from veomni_b200 import ulysses as U
 
@@ -109,18 +131,22 @@ def test_fsdp(rank, world, dev):
     ref_m = build()
     ref_m(x).float().square().mean().backward()
     ref = {n: p.grad.to_local().clone() for n, p in ref_m.named_parameters()}
-    m = build()
-    install_fsdp_comm(m)
-    for step in range(2):  # second step exercises buffer reuse
-        for p in m.parameters():
-            p.grad = None
-        out = m(x)
-        out.float().square().mean().backward()
-    torch.cuda.synchronize()
-    for n, p in m.named_parameters():
-        got = p.grad.to_local()
-        # same bf16 GEMMs; only the fp32 summation order of the reduce-scatter differs from NCCL's ring
-        torch.testing.assert_close(got, ref[n], atol=1e-6, rtol=1e-4, msg=lambda s, n=n: f"fsdp grad {n}: {s}")
+    got = {}
+    for pack in (True, False):  # bf16-packed copy-in + bf16 pull, and torch's fp32 copy-in + fp32 pull
+        m = build()
+        install_fsdp_comm(m, pack_bf16=pack)
+        for step in range(2):  # second step exercises buffer reuse
+            for p in m.parameters():
+                p.grad = None
+            out = m(x)
+            out.float().square().mean().backward()
+        torch.cuda.synchronize()
+        got[pack] = {n: p.grad.to_local().clone() for n, p in m.named_parameters()}
+        for n, g in got[pack].items():
+            # same bf16 GEMMs; only the fp32 summation order of the reduce-scatter differs from NCCL's ring
+            torch.testing.assert_close(g, ref[n], atol=1e-6, rtol=1e-4, msg=lambda s, n=n: f"fsdp grad {n} (pack={pack}): {s}")
+    for n in got[True]:
+        assert torch.equal(got[True][n], got[False][n]), f"bf16-packed reduce-scatter changed the gradient of {n}"
 
 
 def test_ulysses_model(rank, world, dev):
@@ -312,6 +338,9 @@ def bench(symm, rank, world, dev):
     for ctas in (16, 32, 64):
         ms = timeit(lambda: symm.reduce_scatter_f32(inp, o, 1.0 / world, 1, ctas))
         res.append({"kernel": f"fsdp_reducescatter[U=193M fp32,N={world},ctas={ctas}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 4 / ms / 1e6, 1)})
+    for ctas in (16, 32, 64):
+        ms = timeit(lambda: symm.reduce_scatter_bf16(inp, U // world, o, 1.0 / world, 1, ctas))
+        res.append({"kernel": f"fsdp_reducescatter_bf16pull[U=193M,N={world},ctas={ctas}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 2 / ms / 1e6, 1)})
     nci = torch.empty(U, dtype=torch.float32, device=dev)
     ms = timeit(lambda: dist.reduce_scatter_tensor(o, nci, op=dist.ReduceOp.AVG))
     res.append({"kernel": f"(lib) nccl reduce_scatter[U=193M fp32,N={world}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 4 / ms / 1e6, 1)})
@@ -366,6 +395,7 @@ def main():
     stage("barrier x3", lambda: [symm.barrier() for _ in range(3)])
     stage("allgather", test_barrier_and_allgather, symm, rank, world, dev)
     stage("reduce_scatter", test_reduce_scatter, symm, rank, world, dev)
+    stage("reduce_scatter bf16 pull", test_reduce_scatter_bf16, symm, rank, world, dev)
     stage("ulysses", test_ulysses, rank, world, dev)
     stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
     stage("expert parallel dispatch/combine", test_ep, rank, world, dev)

@@ -174,3 +174,47 @@ def test_swiglu_merged_fc1_strided_views(cuda_dev):
     out = F.silu_mul(a, b)
     ra, rb = fc1.chunk(2, dim=-1)
     _close(out, o_ops.silu_mul(ra, rb), atol=1e-2, rtol=8e-3)
+
+
+def test_multi_tensor_sumsq_and_scale(cuda_dev):
+    """Gradient-clip kernels vs torch: ragged sizes (scalar heads/tails, multi-entry tensors), fp32 and bf16,
+    determinism, and the no-op at coefficient 1."""
+    from veomni_b200.clip_grad_norm import multi_scale_, multi_sumsq
+
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    sizes = [1, 3, 4096, 4097, (1 << 20) + 5, 3 * (1 << 20), 12345]
+    for dtype, rtol in ((torch.float32, 2e-6), (torch.bfloat16, 2e-6)):
+        base = torch.randn(sum(sizes) + 3, generator=g, device=cuda_dev).to(dtype)
+        ts, off = [], 1  # offset 1: misaligned starts
+        for n in sizes:
+            ts.append(base[off:off + n])
+            off += n
+        ref = sum((t.double() ** 2).sum() for t in ts)
+        got = multi_sumsq(ts)
+        assert abs(got.double().item() - ref.item()) / ref.item() < rtol
+        assert torch.equal(got, multi_sumsq(ts))
+        before = [t.clone() for t in ts]
+        multi_scale_(ts, torch.ones((), device=cuda_dev))
+        assert all(torch.equal(a, b) for a, b in zip(ts, before))
+        multi_scale_(ts, torch.tensor(0.37, device=cuda_dev))
+        for a, b in zip(ts, before):
+            assert torch.equal(a, (b.float() * torch.tensor(0.37, device=cuda_dev)).to(dtype))
+
+
+def test_clip_grad_norm_matches_torch(cuda_dev):
+    """clip_grad_norm (dense path) against torch.nn.utils.clip_grad_norm_ on the same gradients: norm to 1e-6 rel.,
+    clipped gradients bit-exact up to the coefficient's rounding (rtol 1e-6)."""
+    from veomni_b200.clip_grad_norm import clip_grad_norm
+
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(300, 257), torch.nn.Linear(257, 19)).to(cuda_dev)
+    m2 = torch.nn.Sequential(torch.nn.Linear(300, 257), torch.nn.Linear(257, 19)).to(cuda_dev)
+    m2.load_state_dict(m.state_dict())
+    x = torch.randn(64, 300, device=cuda_dev)
+    for mod in (m, m2):
+        (mod(x) ** 2).sum().backward()
+    total = clip_grad_norm(m, 0.5)
+    ref = torch.nn.utils.clip_grad_norm_(m2.parameters(), 0.5)
+    torch.testing.assert_close(total, ref, atol=0, rtol=1e-6)
+    for a, b in zip(m.parameters(), m2.parameters()):
+        torch.testing.assert_close(a.grad, b.grad, atol=1e-12, rtol=2e-6)

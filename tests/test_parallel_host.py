@@ -101,3 +101,26 @@ def test_symmetric_allocator_bookkeeping():
     ar.release(1024, 2048)
     ar.release(c, sc)
     assert ar.free == [(1024, 4096)] and ar.live == 0
+
+
+def test_pack_plan_reproduces_chunk_cat_layout():
+    """The geometry the bf16 pack kernel uses == torch._chunk_cat(dim=0, num_chunks=world) as FSDP2's
+    foreach_reduce_scatter_copy_in calls it (ragged dim-0 sizes are zero-padded per parameter)."""
+    import torch
+
+    from veomni_b200.fsdp_comm import pack_plan
+
+    g = torch.Generator().manual_seed(0)
+    for world in (2, 4, 8):
+        shapes = [(10, 4), (3,), (7, 2, 2), (16, 8), (1, 5)]
+        grads = [torch.randn(*s, generator=g) for s in shapes]
+        plan, row = pack_plan(shapes, world)
+        ref = torch.empty(world, row)
+        torch._chunk_cat(grads, dim=0, num_chunks=world, out=ref)
+        out = torch.full((world, row), float("nan"))
+        for t, (numel, chunk, off) in zip(grads, plan):
+            flat = torch.cat([t.reshape(-1), torch.zeros(chunk * world - numel)])  # el -> (rank, within) as in the kernel
+            for el in range(chunk * world):
+                r = el // chunk
+                out[r, off + el - r * chunk] = flat[el]
+        assert torch.equal(out, ref), world

@@ -44,6 +44,9 @@ SIGNATURES = {
     "vb200_qknorm_rope_fwd": (c_int, [_P] * 10 + [_I64, _I32, _I32, _I32, _F, _P]),
     "vb200_qknorm_rope_bwd": (c_int, [_P] * 15 + [_I64, _I32, _I32, _I32, _P]),
     "vb200_qknorm_rope_bwd_partials": (_I64, [_I64]),
+    "vb200_multi_sumsq_partials": (c_int64, [_I32]),
+    "vb200_multi_sumsq": (c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),
+    "vb200_multi_scale": (c_int, [_P, _P, _I32, _I32, _P, _P]),
     "vb200_cross_entropy": (c_int, [_P, _I32, _I64, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _I64, _F, _P, _P, _P]),
     "vb200_count_valid_labels": (c_int, [_P, _I64, _I64, _P, _P]),
     "vb200_swiglu_fwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
@@ -70,6 +73,8 @@ SIGNATURES = {
     "vb200_comm_barrier": (c_int, [_P, _I32, _P]),
     "vb200_allgather": (c_int, [_P, _I32, _I64, _I64, _I32, _P]),
     "vb200_reduce_scatter_f32": (c_int, [_P, _I32, _I64, _I64, _F, _P, _I32, _P]),
+    "vb200_reduce_scatter_bf16": (c_int, [_P, _I32, _I64, _I64, _F, _P, _I32, _P]),
+    "vb200_fsdp_pack_bf16": (c_int, [_P, _I32, _I32, _I64, _P, _I32, _P]),
     "vb200_all_to_all": (c_int, [_P, _I32, _I64, _I32, _P, _I32, _P]),
     "vb200_chunk_pull": (c_int, [_P, _I32, _I64, _P, _I32, _P, _I32, _P]),
 }

@@ -157,8 +157,9 @@ allgather_kernel(CommDev c, int ch, int64_t off, int64_t shard_bytes) {
 
 // Reduce-scatter: every rank holds N chunks of `chunk` fp32 values at its buffer; rank r sums chunk r of
 // all ranks in rank order 0..N-1 (deterministic), scales, writes `out` (any memory).
-// W = compile-time world size (0 = generic up to 8), UN = vectors per thread per iteration: UN*W = 8
-// independent 16-byte peer loads are in flight per thread (NVLink latency ~2 us).
+// W = compile-time world size (0 = generic up to 8), UN = vectors per thread per iteration: UN*W = 16
+// independent 16-byte loads are in flight per thread (one of the W sources is local; a loaded NVSwitch round trip
+// measured ~7 us, so 8 in flight left 32 CTAs at half the link rate).
 template <int W, int UN>
 __global__ void __launch_bounds__(512)
 reduce_scatter_f32_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float scale, float* __restrict__ out) {
@@ -225,6 +226,153 @@ reduce_scatter_f32_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float s
     }
 #undef VB_SRC
     if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
+}
+
+// bf16-input variant: the gradients of a bf16 FSDP unit are exact bf16 values, so pulling them as bf16 and
+// accumulating in fp32 in rank order is bit-identical to the fp32 reduce-scatter of their fp32 copies — at half
+// the NVLink bytes and without the fp32 staging pass. Input layout: N chunks of `chunk` bf16 at `off`.
+template <int W, int UN>
+__global__ void __launch_bounds__(512)
+reduce_scatter_bf16_kernel(CommDev c, int ch, int64_t off, int64_t chunk, float scale, float* __restrict__ out) {
+    __shared__ int64_t peer_off[kMaxWorld];
+    const uint32_t e = c.state[ch] + 1;
+    if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
+    wait_peers(c, ch, 0, e, peer_off);
+    constexpr int NP = W ? W : kMaxWorld;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rank_base = (int64_t)c.rank * chunk * 2;
+#define VB_SRC(p) (c.data[p] + peer_off[p] + rank_base)
+    int64_t head = ((16 - ((uintptr_t)VB_SRC(0) & 15)) & 15) >> 1;  // bf16 elements until 16-byte alignment
+    if (head > chunk) head = chunk;
+    const int64_t nvec = (chunk - head) >> 3;
+    const int64_t tail0 = head + (nvec << 3);
+    for (int64_t j = tid; j < head + (chunk - tail0); j += nthr) {
+        const int64_t i = j < head ? j : tail0 + (j - head);
+        float a = 0.f;
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+            if (p < c.world) {
+                uint16_t v;
+                asm volatile("ld.global.u16 %0, [%1];" : "=h"(v) : "l"(VB_SRC(p) + i * 2) : "memory");
+                a += __uint_as_float((uint32_t)v << 16);
+            }
+        out[i] = a * scale;
+    }
+    const bool out_aligned = (((uintptr_t)(out + head)) & 15) == 0;
+    for (int64_t v0 = tid; v0 < nvec; v0 += nthr * UN) {
+        uint4 r[UN][NP];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int64_t v = v0 + (int64_t)u * nthr;
+#pragma unroll
+            for (int p = 0; p < NP; ++p)
+                if (p < c.world && v < nvec) r[u][p] = ldg_v4(VB_SRC(p) + (head << 1) + (v << 4));
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int64_t v = v0 + (int64_t)u * nthr;
+            if (v < nvec) {
+                float a[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = 0.f;
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                    if (p < c.world) {
+                        const uint32_t w[4] = {r[u][p].x, r[u][p].y, r[u][p].z, r[u][p].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            a[2 * i] += __uint_as_float(w[i] << 16);
+                            a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+                        }
+                    }
+                float* o = out + head + v * 8;
+                if (out_aligned) {
+                    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(a[0] * scale), "f"(a[1] * scale), "f"(a[2] * scale), "f"(a[3] * scale) : "memory");
+                    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + 4), "f"(a[4] * scale), "f"(a[5] * scale), "f"(a[6] * scale), "f"(a[7] * scale) : "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) asm volatile("st.global.f32 [%0], %1;" ::"l"(o + i), "f"(a[i] * scale) : "memory");
+                }
+            }
+        }
+    }
+#undef VB_SRC
+    if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
+}
+
+// FSDP2 reduce-scatter copy-in without the dtype conversion: packs the unsharded bf16 gradients of one unit into
+// the [world, S] chunk-major layout torch._chunk_cat produces (chunk r of every parameter, dim-0 zero-padded to a
+// multiple of world, concatenated), keeping bf16. One launch: grid.y = parameter, grid.x blocks stride over it.
+struct PackEntry {
+    const void* src;
+    int64_t numel;   // real elements of the parameter
+    int64_t chunk;   // elements per rank chunk = ceil(dim0 / world) * inner
+    int64_t off;     // element offset of this parameter inside a rank's row of the output
+};
+constexpr int kPackMax = 24;
+struct PackArgs {
+    int n;
+    int world;
+    int64_t row;  // S: elements per rank row
+    PackEntry e[kPackMax];
+};
+
+__device__ __forceinline__ __nv_bfloat16 pack_elem(const __nv_bfloat16* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ __nv_bfloat16 pack_elem(const float* p, int64_t i) { return __float2bfloat16_rn(p[i]); }
+__device__ __forceinline__ uint4 pack_vec8(const __nv_bfloat16* p, int64_t v) { return ldg_stream(p + (v << 3)); }
+__device__ __forceinline__ uint4 pack_vec8(const float* p, int64_t v) {  // 8 fp32 -> 8 bf16 (round to nearest even)
+    const uint4 a = ldg_stream(p + (v << 3)), b = ldg_stream(p + (v << 3) + 4);
+    uint4 r;
+    r.x = f2_to_bf2(__uint_as_float(a.x), __uint_as_float(a.y));
+    r.y = f2_to_bf2(__uint_as_float(a.z), __uint_as_float(a.w));
+    r.z = f2_to_bf2(__uint_as_float(b.x), __uint_as_float(b.y));
+    r.w = f2_to_bf2(__uint_as_float(b.z), __uint_as_float(b.w));
+    return r;
+}
+
+// SrcT = bf16: the reduce-scatter copy-in; SrcT = float: also the all-gather copy-in (world = 1, the fp32 master
+// shards cast to the bf16 all-gather input in one pass).
+template <typename SrcT, bool VEC>
+__global__ void __launch_bounds__(512)
+fsdp_pack_bf16_kernel(PackArgs a, __nv_bfloat16* __restrict__ out) {
+    const PackEntry& e = a.e[blockIdx.y];
+    const SrcT* src = reinterpret_cast<const SrcT*>(e.src);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const int64_t padded = e.chunk * a.world;
+    if (VEC) {  // chunk, off, row multiples of 8 and 16-byte aligned pointers: 8 elements per thread step
+        const int64_t nvec = padded >> 3;
+        const int64_t full = e.numel >> 3;  // vectors entirely inside the real data
+        for (int64_t v0 = tid; v0 < nvec; v0 += 4 * nthr) {
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t v = v0 + u * nthr;
+                if (v < full) r[u] = pack_vec8(src, v);
+                else if (v < nvec) {
+                    __align__(16) __nv_bfloat16 t[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t[i] = ((v << 3) + i < e.numel) ? pack_elem(src, (v << 3) + i) : __float2bfloat16_rn(0.f);
+                    r[u] = *reinterpret_cast<uint4*>(t);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t v = v0 + u * nthr;
+                if (v < nvec) {
+                    const int64_t el = v << 3;
+                    const int64_t rk = el / e.chunk;
+                    stg_v4(out + rk * a.row + e.off + (el - rk * e.chunk), r[u]);
+                }
+            }
+        }
+    } else {
+        for (int64_t el = tid; el < padded; el += nthr) {
+            const int64_t rk = el / e.chunk;
+            out[rk * a.row + e.off + (el - rk * e.chunk)] = el < e.numel ? pack_elem(src, el) : __float2bfloat16_rn(0.f);
+        }
+    }
 }
 
 // Chunked pull ("all-to-all"): for each descriptor d and each peer p, copy `rows` segments of
@@ -437,12 +585,73 @@ extern "C" int vb200_reduce_scatter_f32(void* comm, int32_t channel, int64_t reg
     cudaStream_t st = (cudaStream_t)stream;
     switch (h->dev.world) {
         case 1: reduce_scatter_f32_kernel<1, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
-        case 2: reduce_scatter_f32_kernel<2, 4><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
-        case 4: reduce_scatter_f32_kernel<4, 2><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
-        default: reduce_scatter_f32_kernel<0, 1><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        case 2: reduce_scatter_f32_kernel<2, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        case 4: reduce_scatter_f32_kernel<4, 4><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        default: reduce_scatter_f32_kernel<0, 2><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
     }
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_reduce_scatter_bf16(void* comm, int32_t channel, int64_t region_offset, int64_t chunk_elems,
+                                         float scale, float* out, int32_t num_ctas, void* stream) {
+    if (check_ch(channel)) return VB200_EINVAL;
+    CommHost* h = (CommHost*)comm;
+    if (region_offset < 0 || (region_offset & 255) || chunk_elems < 0 ||
+        region_offset + chunk_elems * 2 * h->dev.world > h->data_bytes)
+        return vb200_set_error(VB200_EINVAL, "reduce_scatter_bf16: offset must be 256-byte aligned and inside the region");
+    const int g = clamp_ctas(num_ctas);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->dev.world) {
+        case 1: reduce_scatter_bf16_kernel<1, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        case 2: reduce_scatter_bf16_kernel<2, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        case 4: reduce_scatter_bf16_kernel<4, 4><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+        default: reduce_scatter_bf16_kernel<0, 2><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
+    }
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+// desc: n x 4 int64 (src pointer, numel, chunk elements, row offset); out: [world, row_elems] bf16
+extern "C" int vb200_fsdp_pack_bf16(const int64_t* desc, int32_t n, int32_t world, int64_t row_elems, void* out,
+                                    int32_t src_dtype, void* stream) {
+    if (n < 0 || world <= 0 || row_elems < 0 || (n > 0 && (!desc || !out)) || (src_dtype != 0 && src_dtype != 1))
+        return vb200_set_error(VB200_EINVAL, "fsdp_pack_bf16: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int base = 0; base < n; base += kPackMax) {
+        PackArgs a;
+        a.n = n - base < kPackMax ? n - base : kPackMax;
+        a.world = world;
+        a.row = row_elems;
+        bool vec = (row_elems % 8 == 0) && (((uintptr_t)out & 15) == 0);
+        int64_t biggest = 0;
+        for (int i = 0; i < a.n; ++i) {
+            const int64_t* d = desc + (int64_t)(base + i) * 4;
+            a.e[i].src = (const void*)(uintptr_t)d[0];
+            a.e[i].numel = d[1];
+            a.e[i].chunk = d[2];
+            a.e[i].off = d[3];
+            if (d[1] < 0 || d[2] <= 0 || d[3] < 0 || d[3] + d[2] > row_elems || d[1] > d[2] * world)
+                return vb200_set_error(VB200_EINVAL, "fsdp_pack_bf16: inconsistent descriptor");
+            vec = vec && d[2] % 8 == 0 && d[3] % 8 == 0 && ((uintptr_t)d[0] & 15) == 0;
+            if (d[2] * world > biggest) biggest = d[2] * world;
+        }
+        int64_t blocks = (biggest / 8 + 512 * 4 - 1) / (512 * 4);
+        if (blocks < 1) blocks = 1;
+        if (blocks > 148 * 2) blocks = 148 * 2;
+        dim3 grid((unsigned)blocks, (unsigned)a.n);
+        if (src_dtype == 0) {
+            if (vec) fsdp_pack_bf16_kernel<__nv_bfloat16, true><<<grid, 512, 0, st>>>(a, (__nv_bfloat16*)out);
+            else fsdp_pack_bf16_kernel<__nv_bfloat16, false><<<grid, 512, 0, st>>>(a, (__nv_bfloat16*)out);
+        } else {
+            if (vec) fsdp_pack_bf16_kernel<float, true><<<grid, 512, 0, st>>>(a, (__nv_bfloat16*)out);
+            else fsdp_pack_bf16_kernel<float, false><<<grid, 512, 0, st>>>(a, (__nv_bfloat16*)out);
+        }
+        vb200_count_launch(1);
+        VB_HOST_CHECK_LAUNCH();
+    }
     return VB200_OK;
 }
 

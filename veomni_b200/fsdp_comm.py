@@ -64,11 +64,25 @@ class B200AllGather(AllGather):
         return None
 
 
+# reduce-scatter inputs handed out by B200ReduceScatter.allocate, by address: lets the patched copy-in recognise them
+_RS_INPUTS: dict[int, "B200ReduceScatter"] = {}
+
+
 class B200ReduceScatter(ReduceScatter):
-    def __init__(self, symm: SymmetricMemory, num_ctas: int = 32):
+    """FSDP2 unit reduce-scatter on the NVLink pull kernel.
+
+    With ``pack_bf16`` (default) the copy-in that precedes it is ours as well (:func:`_copy_in`): bf16 gradients are
+    packed into the chunk-major layout *as bf16* and the kernel accumulates them in fp32 — the same sums in the same
+    order as the fp32 path, without the fp32 staging pass (``chunk_cat``: 25.6 ms of a 337 ms Qwen3-8B step) and at
+    half the NVLink bytes.
+    """
+
+    def __init__(self, symm: SymmetricMemory, num_ctas: int = 32, pack_bf16: bool = True):
         self.symm = symm
         self.num_ctas = num_ctas
+        self.pack_bf16 = pack_bf16
         self._next_is_input = True
+        self._packed: dict[int, int] = {}  # input address -> bf16 elements per rank chunk
 
     def allocate(self, size: Sequence[int], *, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
         # foreach_reduce (_fsdp_collectives.py:522-541) asks for the (N*chunk) input first and for the
@@ -77,7 +91,10 @@ class B200ReduceScatter(ReduceScatter):
         shape = tuple(int(s) for s in size)
         if self._next_is_input:
             self._next_is_input = False
-            return self.symm.empty(shape, dtype, arena="fsdp_rs")
+            t = self.symm.empty(shape, dtype, arena="fsdp_rs")
+            _RS_INPUTS[t.data_ptr()] = self
+            self._packed.pop(t.data_ptr(), None)
+            return t
         self._next_is_input = True
         return torch.empty(shape, dtype=dtype, device=device)
 
@@ -89,6 +106,13 @@ class B200ReduceScatter(ReduceScatter):
             raise VB200Error(
                 f"B200 reduce-scatter reduces in fp32 (VeOmni's default reduce_dtype, arguments_types.py:248-255); got {input_tensor.dtype}"
             )
+        chunk = self._packed.pop(input_tensor.data_ptr(), None)
+        if chunk is not None:  # our copy-in left bf16 gradients in the first half of this buffer
+            if chunk * world != input_tensor.numel():
+                raise VB200Error("reduce-scatter: packed gradient size does not match the input tensor")
+            self.symm.reduce_scatter_bf16(input_tensor, chunk, output_tensor, _reduce_scale(op, world), CH_REDUCE_SCATTER,
+                                          self.num_ctas)
+            return None
         if not self.symm.contains(input_tensor):  # allocate() order assumption broken: stay correct
             staged = self.symm.empty(tuple(input_tensor.shape), input_tensor.dtype, arena="fsdp_rs")
             staged.copy_(input_tensor)
@@ -96,6 +120,112 @@ class B200ReduceScatter(ReduceScatter):
         self.symm.reduce_scatter_f32(input_tensor, output_tensor, _reduce_scale(op, world), CH_REDUCE_SCATTER,
                                      self.num_ctas)
         return None
+
+
+def pack_plan(shapes: list[tuple[int, ...]], world: int):
+    """Geometry of torch._chunk_cat(grads, dim=0, num_chunks=world): per parameter (numel, chunk elements, row offset)
+    and the row length S. Host-only (tests/test_parallel_host.py checks it against chunk_cat itself)."""
+    plan, off = [], 0
+    for shp in shapes:
+        d0 = shp[0] if len(shp) else 1
+        inner = 1
+        for x in shp[1:]:
+            inner *= x
+        chunk = (d0 + world - 1) // world * inner
+        plan.append((d0 * inner, chunk, off))
+        off += chunk
+    return plan, off
+
+
+_orig_copy_in = None
+_orig_div = None
+
+
+def _copy_in(unsharded_grads, reduce_scatter_input, world_size):
+    """Drop-in for torch's foreach_reduce_scatter_copy_in (_fsdp_collectives.py:667-675)."""
+    comm = _RS_INPUTS.get(reduce_scatter_input.data_ptr())
+    ok = (comm is not None and comm.pack_bf16 and world_size > 1 and reduce_scatter_input.dtype == torch.float32
+          and all(g.is_cuda and g.dtype == torch.bfloat16 and g.is_contiguous() for g in unsharded_grads))
+    if not ok:
+        return _orig_copy_in(unsharded_grads, reduce_scatter_input, world_size)
+    plan, row = pack_plan([tuple(g.shape) for g in unsharded_grads], world_size)
+    if row * world_size != reduce_scatter_input.numel():
+        return _orig_copy_in(unsharded_grads, reduce_scatter_input, world_size)
+    import ctypes
+
+    from . import _lib
+    from ._lib import check, stream_ptr
+
+    flat = []
+    for g, (numel, chunk, off) in zip(unsharded_grads, plan):
+        flat += [g.data_ptr(), numel, chunk, off]
+    arr = (ctypes.c_int64 * len(flat))(*flat)
+    with torch.cuda.device(reduce_scatter_input.device):
+        check(_lib.load().vb200_fsdp_pack_bf16(arr, len(plan), world_size, row, reduce_scatter_input.data_ptr(), 0, stream_ptr()),
+              "vb200_fsdp_pack_bf16")
+    comm._packed[reduce_scatter_input.data_ptr()] = row
+    return None
+
+
+def _div_if_needed(tensor, div_factor):
+    comm = _RS_INPUTS.get(tensor.data_ptr())
+    if div_factor is not None and div_factor != 1 and comm is not None and tensor.data_ptr() in comm._packed:
+        raise VB200Error("B200 reduce-scatter: a pre-divide factor on bf16-packed gradients is not supported "
+                         "(use reduce_dtype=float32 without a custom divide factor, or pack_bf16=False)")
+    return _orig_div(tensor, div_factor)
+
+
+_ag_lib = None
+
+
+def _ag_copy_in(all_gather_inputs, all_gather_output, inp_split_sizes, all_gather_input_numel, rank):
+    """CUDA implementation of the ``fsdp::all_gather_copy_in`` op (all_gather_copy_in_cuda,
+    _fsdp_collectives.py:175-188): the local shards (fp32 masters under mixed precision) written, cast to bf16, into
+    this rank's slice of the all-gather buffer — one multi-tensor kernel instead of chunked ``_foreach_copy_``
+    launches (measured 1.7 TB/s on Qwen3-8B). Anything but fp32/bf16 sources into a bf16 buffer takes torch's path."""
+    all_gather_input = all_gather_output.narrow(0, all_gather_input_numel * rank, all_gather_input_numel)
+    srcs = all_gather_inputs
+    ok = (all_gather_output.is_cuda and all_gather_output.dtype == torch.bfloat16 and len(srcs) > 0
+          and len({t.dtype for t in srcs}) == 1 and srcs[0].dtype in (torch.float32, torch.bfloat16)
+          and all(t.is_cuda and t.is_contiguous() for t in srcs)
+          and all(t.numel() == n for t, n in zip(srcs, inp_split_sizes)) and sum(inp_split_sizes) == all_gather_input_numel)
+    if not ok:
+        with torch.no_grad():
+            torch._foreach_copy_(torch.split(all_gather_input, inp_split_sizes), srcs)
+        return all_gather_input, all_gather_output
+    import ctypes
+
+    from . import _lib
+    from ._lib import check, stream_ptr
+
+    flat, off = [], 0
+    for t in srcs:
+        n = t.numel()
+        if n:
+            flat += [t.data_ptr(), n, n, off]
+        off += n
+    arr = (ctypes.c_int64 * len(flat))(*flat)
+    with torch.cuda.device(all_gather_output.device):
+        check(_lib.load().vb200_fsdp_pack_bf16(arr, len(flat) // 4, 1, all_gather_input_numel, all_gather_input.data_ptr(),
+                                               0 if srcs[0].dtype == torch.bfloat16 else 1, stream_ptr()),
+              "vb200_fsdp_pack_bf16")
+    return all_gather_input, all_gather_output
+
+
+def _patch_copy_in() -> None:
+    """Route FSDP2's reduce-scatter copy-in through :func:`_copy_in`. ``foreach_reduce`` looks both names up in its
+    module at call time, so replacing the module attributes is enough."""
+    global _orig_copy_in, _orig_div
+    from torch.distributed.fsdp._fully_shard import _fsdp_collectives as fc
+
+    if _orig_copy_in is None:
+        _orig_copy_in, _orig_div = fc.foreach_reduce_scatter_copy_in, fc._div_if_needed
+        fc.foreach_reduce_scatter_copy_in = _copy_in
+        fc._div_if_needed = _div_if_needed
+        # the all-gather copy-in is a registered op: override its CUDA kernel
+        global _ag_lib
+        _ag_lib = torch.library.Library("fsdp", "IMPL")
+        _ag_lib.impl("all_gather_copy_in", _ag_copy_in, "CUDA", allow_override=True)
 
 
 def plan_fsdp_region(model: torch.nn.Module, world: int, param_bytes: int = 2, reduce_bytes: int = 4):
@@ -135,7 +265,7 @@ def plan_fsdp_region(model: torch.nn.Module, world: int, param_bytes: int = 2, r
 
 
 def install_fsdp_comm(model: torch.nn.Module, group: dist.ProcessGroup | None = None, symm: SymmetricMemory | None = None,
-                      num_ctas: int = 32) -> SymmetricMemory:
+                      num_ctas: int = 32, pack_bf16: bool = True) -> SymmetricMemory:
     """Swap every FSDP2 unit of ``model`` onto the NVLink pull collectives.
 
     Call right after ``build_parallelize_model`` returns (veomni/trainer/base.py:387-404).
@@ -146,7 +276,9 @@ def install_fsdp_comm(model: torch.nn.Module, group: dist.ProcessGroup | None = 
         g = group if group is not None else dist.group.WORLD
         total, arenas = plan_fsdp_region(model, dist.get_world_size(g))
         symm = get_symmetric_memory(g, total, arenas)
-    ag, rs = B200AllGather(symm, num_ctas), B200ReduceScatter(symm, num_ctas)
+    ag, rs = B200AllGather(symm, num_ctas), B200ReduceScatter(symm, num_ctas, pack_bf16)
+    if pack_bf16:
+        _patch_copy_in()
     n = 0
     for m in model.modules():
         if isinstance(m, FSDPModule):

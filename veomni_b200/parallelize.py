@@ -45,4 +45,10 @@ def build_parallelize_model(
     fully_shard(model, mesh=mesh, mp_policy=mp)
     if b200_comm:
         model._vb200_symm = install_fsdp_comm(model, mesh.get_group(), num_ctas=comm_ctas)
+    # the reference binds the FSDP2-aware clip onto the model (torch_parallelize.py:412-414)
+    import types
+
+    from .clip_grad_norm import clip_grad_norm
+
+    model.clip_grad_norm_ = types.MethodType(clip_grad_norm, model)
     return model

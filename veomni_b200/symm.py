@@ -179,6 +179,14 @@ class SymmetricMemory:
                                                      out.data_ptr(), num_ctas, _lib.stream_ptr()),
                   "vb200_reduce_scatter_f32")
 
+    def reduce_scatter_bf16(self, inp: torch.Tensor, chunk: int, out: torch.Tensor, scale: float, channel: int,
+                            num_ctas: int = 32) -> None:
+        """``inp``: a tensor of this region whose first ``world * chunk`` bf16 elements are the packed gradients."""
+        with torch.cuda.device(self.device):
+            check(self._lib.vb200_reduce_scatter_bf16(self.comm, channel, self.offset_of(inp), chunk, float(scale),
+                                                      out.data_ptr(), num_ctas, _lib.stream_ptr()),
+                  "vb200_reduce_scatter_bf16")
+
     def all_to_all(self, base: torch.Tensor, descs: list[tuple], channel: int, num_ctas: int = 32) -> None:
         """descs: (src_off, src_rank_stride, src_row_stride, dst_ptr, dst_peer_stride, dst_row_stride, rows, seg_bytes)
         with src offsets relative to ``base`` (a tensor in this region)."""
