@@ -176,6 +176,39 @@ def _div_if_needed(tensor, div_factor):
 
 
 _ag_lib = None
+_orig_get_inputs = None
+# bf16 placeholder (address) -> the fp32 master shard it stands for, set by _param_all_gather_inputs and consumed by
+# _ag_copy_in within the same foreach_all_gather call
+_AG_SOURCES: dict[int, torch.Tensor] = {}
+
+
+def _param_all_gather_inputs(fsdp_params):
+    """Replacement for torch's _get_param_all_gather_inputs (_fsdp_collectives.py:295-343). The original casts the fp32
+    master shards into a flat bf16 temporary (``_foreach_copy_``) which ``all_gather_copy_in`` then copies again into
+    the all-gather buffer; here the flat temporary is only *allocated* — it gives FSDP the dtype / numel metadata it
+    derives from the inputs — and the fp32 shards are remembered so :func:`_ag_copy_in` can cast them straight into the
+    all-gather buffer (one pass of 4 + 2 bytes per parameter instead of 4 + 2 + 2 + 2)."""
+    from torch.distributed.fsdp._fully_shard._fsdp_common import compiled_autograd_enabled
+    from torch.distributed.fsdp._fully_shard._fsdp_param import ShardedState
+
+    def fast(p) -> bool:
+        return (p.param_dtype == torch.bfloat16 and not p.offload_to_cpu
+                and not hasattr(p._sharded_local_tensor, "fsdp_pre_all_gather"))
+
+    if _ag_lib is None or compiled_autograd_enabled() or not all(fast(p) for p in fsdp_params):
+        return _orig_get_inputs(fsdp_params)
+    srcs = [p._sharded_param_data if p.sharded_state == ShardedState.SHARDED else p._sharded_post_forward_param_data
+            for p in fsdp_params]
+    if not all(t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.bfloat16) for t in srcs):
+        return _orig_get_inputs(fsdp_params)
+    numels = [t.numel() for t in srcs]
+    flat = torch.empty((sum(numels),), device=srcs[0].device, dtype=torch.bfloat16)  # never written or read
+    splits = torch.split(flat, numels)
+    _AG_SOURCES.clear()
+    for sp, t in zip(splits, srcs):
+        if t.numel():
+            _AG_SOURCES[sp.data_ptr()] = t
+    return [[sp] for sp in splits]
 
 
 def _ag_copy_in(all_gather_inputs, all_gather_output, inp_split_sizes, all_gather_input_numel, rank):
@@ -184,10 +217,10 @@ def _ag_copy_in(all_gather_inputs, all_gather_output, inp_split_sizes, all_gathe
     this rank's slice of the all-gather buffer — one multi-tensor kernel instead of chunked ``_foreach_copy_``
     launches (measured 1.7 TB/s on Qwen3-8B). Anything but fp32/bf16 sources into a bf16 buffer takes torch's path."""
     all_gather_input = all_gather_output.narrow(0, all_gather_input_numel * rank, all_gather_input_numel)
-    srcs = all_gather_inputs
+    srcs = [_AG_SOURCES.pop(t.data_ptr(), t) if t.numel() else t for t in all_gather_inputs]
+    _AG_SOURCES.clear()
     ok = (all_gather_output.is_cuda and all_gather_output.dtype == torch.bfloat16 and len(srcs) > 0
-          and len({t.dtype for t in srcs}) == 1 and srcs[0].dtype in (torch.float32, torch.bfloat16)
-          and all(t.is_cuda and t.is_contiguous() for t in srcs)
+          and all(t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.bfloat16) for t in srcs)
           and all(t.numel() == n for t, n in zip(srcs, inp_split_sizes)) and sum(inp_split_sizes) == all_gather_input_numel)
     if not ok:
         with torch.no_grad():
@@ -198,17 +231,19 @@ def _ag_copy_in(all_gather_inputs, all_gather_output, inp_split_sizes, all_gathe
     from . import _lib
     from ._lib import check, stream_ptr
 
-    flat, off = [], 0
-    for t in srcs:
-        n = t.numel()
-        if n:
-            flat += [t.data_ptr(), n, n, off]
-        off += n
-    arr = (ctypes.c_int64 * len(flat))(*flat)
-    with torch.cuda.device(all_gather_output.device):
-        check(_lib.load().vb200_fsdp_pack_bf16(arr, len(flat) // 4, 1, all_gather_input_numel, all_gather_input.data_ptr(),
-                                               0 if srcs[0].dtype == torch.bfloat16 else 1, stream_ptr()),
-              "vb200_fsdp_pack_bf16")
+    lib = _lib.load()
+    for dt, code in ((torch.bfloat16, 0), (torch.float32, 1)):  # one launch per source dtype
+        flat, off = [], 0
+        for t in srcs:
+            n = t.numel()
+            if n and t.dtype == dt:
+                flat += [t.data_ptr(), n, n, off]
+            off += n
+        if flat:
+            arr = (ctypes.c_int64 * len(flat))(*flat)
+            with torch.cuda.device(all_gather_output.device):
+                check(lib.vb200_fsdp_pack_bf16(arr, len(flat) // 4, 1, all_gather_input_numel, all_gather_input.data_ptr(), code,
+                                               stream_ptr()), "vb200_fsdp_pack_bf16")
     return all_gather_input, all_gather_output
 
 
@@ -223,9 +258,11 @@ def _patch_copy_in() -> None:
         fc.foreach_reduce_scatter_copy_in = _copy_in
         fc._div_if_needed = _div_if_needed
         # the all-gather copy-in is a registered op: override its CUDA kernel
-        global _ag_lib
+        global _ag_lib, _orig_get_inputs
         _ag_lib = torch.library.Library("fsdp", "IMPL")
         _ag_lib.impl("all_gather_copy_in", _ag_copy_in, "CUDA", allow_override=True)
+        _orig_get_inputs = fc._get_param_all_gather_inputs
+        fc._get_param_all_gather_inputs = _param_all_gather_inputs
 
 
 def plan_fsdp_region(model: torch.nn.Module, world: int, param_bytes: int = 2, reduce_bytes: int = 4):
