@@ -207,3 +207,27 @@ def test_attention_tcgen05_backward_matches_mma_full_size(cuda_dev):
     for name, a, b in zip(("dq", "dk", "dv"), res["tc"], res["mma"]):
         s = max(1.0, float(b.float().abs().max()))
         torch.testing.assert_close(a.float() / s, b.float() / s, atol=1e-2, rtol=2e-2, msg=lambda m, n=name: f"{n}: {m}")
+
+
+def test_attention_tcgen05_dq_operand_variants_agree(cuda_dev):
+    """The dQ kernel with Q / dO as TMEM-resident A operands (default) and the all-shared-memory-operand variant issue the
+    same MMAs on the same data: bit-identical dQ, on ragged lengths and at the Qwen3-8B size."""
+    from veomni_b200 import attention as A
+
+    old = (A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS)
+    try:
+        A.FWD_IMPL = A.BWD_IMPL = "tc"
+        for lens, Hq, Hk in (([1, 63, 64, 65, 127, 129, 300], 4, 2), ([4096], 32, 8)):
+            T = sum(lens)
+            g = torch.Generator().manual_seed(T)
+            q, k, v, do = (torch.randn(T, h, 128, generator=g).to(BF).to(cuda_dev) for h in (Hq, Hk, Hk, Hq))
+            cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
+            grads = {}
+            for ss in (False, True):
+                A.BWD_DQ_SS = ss
+                qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+                A.flash_attn_varlen(qq, kk, vv, cu, max(lens)).backward(do)
+                grads[ss] = qq.grad
+            assert torch.equal(grads[False], grads[True]), lens
+    finally:
+        A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS = old

@@ -301,27 +301,38 @@ struct AttnTcBwdParams {
     const float* delta;  // [Hq, total]
     __nv_bfloat16 *dq, *dk, *dv;
     int64_t dq_st, dq_sh, dk_st, dk_sh, dv_st, dv_sh;
+    const __nv_bfloat16 *q, *dout;  // raw pointers: the dQ kernel keeps its Q / dO tile in TMEM (A operands)
+    int64_t q_st, q_sh, do_st, do_sh;
 };
 
 constexpr int TB_N = 64;                      // streamed tile rows
 constexpr int TB_SMALL = TB_N * TC_D * 2;     // 16 KB: a [64][128] bf16 tile (two 8 KB boxes)
 constexpr int TB_DS = 128 * TB_N * 2;         // 16 KB: a [128][64] bf16 tile (one box)
 
-constexpr int TB_KV = 4;  // K/V smem ring depth of the dQ kernel: K_j is held from S_j until dQ_j retires, and
-                          // the refill is a ~1 us TMA round trip — 2 stages left the tensor pipe idle 75 % of the time
-enum { Q_LOAD = 0, Q_KFULL = 1, Q_VFULL = 5, Q_KEMPTY = 9, Q_VEMPTY = 13, Q_SPFULL = 17, Q_SEMPTY = 19, Q_DSFULL = 21,
-       Q_DSEMPTY = 23, Q_DONE = 25, Q_COUNT = 26 };
+// K/V smem ring depth of the dQ kernel: K_j is held from S_j until dQ_j retires, and the refill is a ~1 us TMA round
+// trip — 2 stages left the tensor pipe idle 75 % of the time. With the Q / dO tile in TMEM (TS) their 64 KB of smem
+// go to the ring.
+constexpr int TB_KV_SS = 4, TB_KV_TS = 6, TB_KV_MAX = 6;
+enum { Q_LOAD = 0, Q_KFULL = 1, Q_VFULL = Q_KFULL + TB_KV_MAX, Q_KEMPTY = Q_VFULL + TB_KV_MAX, Q_VEMPTY = Q_KEMPTY + TB_KV_MAX,
+       Q_SPFULL = Q_VEMPTY + TB_KV_MAX, Q_SEMPTY = Q_SPFULL + 2, Q_DSFULL = Q_SEMPTY + 2, Q_DSEMPTY = Q_DSFULL + 2,
+       Q_DONE = Q_DSEMPTY + 2, Q_COUNT = Q_DONE + 1 };
 
+// TS = true: the A operands of S = Q K^T and dP = dO V^T (the CTA's resident Q and dO tiles) live in TMEM instead of
+// shared memory. The SS version moves ~176 KB through shared memory per 128x64 tile (A re-read for every tile) for
+// 768 clk of MMA and is bound by the 128 B/clk shared-memory pipe (ncu: 57 % of it with the tensor pipe at 37 %);
+// with A in TMEM it is ~112 KB and the N=64 MMAs run at their 32-clk floor instead of 48.
+template <bool TS>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const AttnTcBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sQ = smem;                    // 32 KB
-    uint8_t* sdO = sQ + TC_TILE;           // 32 KB
-    uint8_t* sK = sdO + TC_TILE;           // TB_KV x 16 KB
-    uint8_t* sV = sK + TB_KV * TB_SMALL;   // TB_KV x 16 KB
-    uint8_t* sdS = sV + TB_KV * TB_SMALL;  // 2 x 16 KB
+    constexpr int TB_KV = TS ? TB_KV_TS : TB_KV_SS;
+    uint8_t* sQ = smem;                           // 32 KB (SS only)
+    uint8_t* sdO = sQ + (TS ? 0 : TC_TILE);       // 32 KB (SS only)
+    uint8_t* sK = sdO + (TS ? 0 : TC_TILE);       // TB_KV x 16 KB
+    uint8_t* sV = sK + TB_KV * TB_SMALL;          // TB_KV x 16 KB
+    uint8_t* sdS = sV + TB_KV * TB_SMALL;         // 2 x 16 KB
     uint64_t* bar = reinterpret_cast<uint64_t*>(sdS + 2 * TB_DS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + Q_COUNT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -337,7 +348,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Q_COUNT; ++i) {
-            const bool by_warps = (i >= Q_SEMPTY && i < Q_SEMPTY + 2) || (i >= Q_DSFULL && i < Q_DSFULL + 2);
+            const bool by_warps = (i >= Q_SEMPTY && i < Q_SEMPTY + 2) || (i >= Q_DSFULL && i < Q_DSFULL + 2) ||
+                                  (TS && i == Q_LOAD);
             mbar_init(&bar[i], by_warps ? 8 : 1);
         }
         mbar_fence_init();
@@ -347,14 +359,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // TMEM columns: S[2] 0/64, dP[2] 128/192, dQ 256..383
+    // TMEM columns: S[2] 0/64, dP[2] 128/192, dQ 256..383; TS: Q (bf16 A operand) 384..447, dO 448..511
 
     if (warp == 0) {
         if (elect_one_sync()) {
-            mbar_expect_tx(&bar[Q_LOAD], 2 * TC_TILE);
-            for (int hf = 0; hf < 2; ++hf) {
-                tma_load_3d(sQ + hf * TC_BM * 128, &tmQ, hf * 64, h, s0 + m0, &bar[Q_LOAD]);
-                tma_load_3d(sdO + hf * TC_BM * 128, &tmdO, hf * 64, h, s0 + m0, &bar[Q_LOAD]);
+            if (!TS) {
+                mbar_expect_tx(&bar[Q_LOAD], 2 * TC_TILE);
+                for (int hf = 0; hf < 2; ++hf) {
+                    tma_load_3d(sQ + hf * TC_BM * 128, &tmQ, hf * 64, h, s0 + m0, &bar[Q_LOAD]);
+                    tma_load_3d(sdO + hf * TC_BM * 128, &tmdO, hf * 64, h, s0 + m0, &bar[Q_LOAD]);
+                }
             }
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j % TB_KV;
@@ -390,15 +404,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
                         const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16_bo(tmem + st * TB_N, q_addr >> 4, a_off, 16, 1024, k_addr >> 4, b_off, 16, 1024,
-                                    idesc_nt, k ? 1u : 0u);
+                        if (TS)  // A = Q rows in TMEM: 16 bf16 of K per step = 8 columns
+                            umma_f16_ts(tmem + st * TB_N, tmem + 384 + k * 8, k_addr >> 4, b_off, 16, 1024, idesc_nt, k ? 1u : 0u);
+                        else
+                            umma_f16_bo(tmem + st * TB_N, q_addr >> 4, a_off, 16, 1024, k_addr >> 4, b_off, 16, 1024,
+                                        idesc_nt, k ? 1u : 0u);
                     }
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
                         const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
                         const uint32_t b_off = (uint32_t)(k >> 2) * (TB_N * 128) + (uint32_t)(k & 3) * 32;
-                        umma_f16_bo(tmem + 128 + st * TB_N, do_addr >> 4, a_off, 16, 1024, v_addr >> 4, b_off, 16, 1024,
-                                    idesc_nt, k ? 1u : 0u);
+                        if (TS)
+                            umma_f16_ts(tmem + 128 + st * TB_N, tmem + 448 + k * 8, v_addr >> 4, b_off, 16, 1024, idesc_nt, k ? 1u : 0u);
+                        else
+                            umma_f16_bo(tmem + 128 + st * TB_N, do_addr >> 4, a_off, 16, 1024, v_addr >> 4, b_off, 16, 1024,
+                                        idesc_nt, k ? 1u : 0u);
                     }
                     umma_commit(&bar[Q_VEMPTY + ks]);
                     umma_commit(&bar[Q_SPFULL + st]);
@@ -436,6 +456,28 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const float l = p.lse[(int64_t)h * p.total + s0 + m];
             lse2 = (l == -INFINITY) ? 0.f : l * kLog2eTc;
             dl = p.delta[(int64_t)h * p.total + s0 + m];
+        }
+        if (TS) {
+            // this thread's Q row (warps 2-5) or dO row (warps 6-9): 256 contiguous bytes, global -> registers -> TMEM;
+            // two bf16 per 32-bit column is exactly the K-major A-operand layout
+            const __nv_bfloat16* src = cw == 0 ? p.q + (int64_t)(s0 + m) * p.q_st + (int64_t)h * p.q_sh
+                                               : p.dout + (int64_t)(s0 + m) * p.do_st + (int64_t)h * p.do_sh;
+            const uint32_t dst = lane_base + 384 + cw * 64;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t w[32];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (m < L) v = *reinterpret_cast<const uint4*>(src + half * 64 + g * 8);
+                    w[g * 4] = v.x; w[g * 4 + 1] = v.y; w[g * 4 + 2] = v.z; w[g * 4 + 3] = v.w;
+                }
+                tmem_st32(dst + half * 32, w);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[Q_LOAD]);
         }
         for (int j = 0; j < n_tiles; ++j) {
             const int st = j & 1;
@@ -806,8 +848,9 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
                                         int32_t k_heads, int32_t head_dim, const int64_t* st, float scale, int32_t causal,
                                         void* stream) {
     // st: (tok, head) strides of q, k, v, dout, dq, dk, dv.  causal bit 0 = causal; bits 8/9 = run only the
-    // dQ / only the dK-dV kernel (used to time the two kernels separately; 0 = both).
+    // dQ / only the dK-dV kernel (used to time the two kernels separately; 0 = both); bit 10 = SS-operand dQ kernel.
     const int only = (causal >> 8) & 3;
+    const bool ss_operands = (causal >> 10) & 1;  // bit 10: all MMA operands from shared memory (cross-check variant)
     causal &= 1;
     if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: head_dim must be 128");
     if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: Hq % Hk != 0");
@@ -830,11 +873,15 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     p.dq = (__nv_bfloat16*)dq; p.dq_st = st[8]; p.dq_sh = st[9];
     p.dk = (__nv_bfloat16*)dk; p.dk_st = st[10]; p.dk_sh = st[11];
     p.dv = (__nv_bfloat16*)dv; p.dv_st = st[12]; p.dv_sh = st[13];
-    const size_t smem_dq = 2 * TC_TILE + 2 * TB_KV * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
+    p.q = (const __nv_bfloat16*)q; p.q_st = st[0]; p.q_sh = st[1];
+    p.dout = (const __nv_bfloat16*)dout; p.do_st = st[6]; p.do_sh = st[7];
+    const size_t smem_dq = 2 * TC_TILE + 2 * TB_KV_SS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
+    const size_t smem_dq_ts = 2 * TB_KV_TS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
     const size_t smem_kv = 2 * TC_TILE + 2 * TB_QS * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
     static bool attr = false;
     if (!attr) {
-        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq_ts));
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
         attr = true;
     }
@@ -843,7 +890,8 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     p.nseq = num_seqs;
     dim3 gq(p.tiles * q_heads * num_seqs);
     if (only != 2) {
-        attn_bwd_dq_tc_kernel<<<gq, 320, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        if (ss_operands) attn_bwd_dq_tc_kernel<false><<<gq, 320, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        else attn_bwd_dq_tc_kernel<true><<<gq, 320, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         vb200_count_launch(1);
         VB_HOST_CHECK_LAUNCH();
     }

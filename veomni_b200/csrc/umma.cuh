@@ -50,6 +50,19 @@ __device__ __forceinline__ void umma_f16_bo(uint32_t tmem_d, uint32_t a16, uint3
         ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from TMEM (K-major only: lane = row m, each 32-bit column holds two consecutive K elements), B from smem.
+// PTX form as in cute::SM100_MMA_F16BF16_TS (cute/arch/mma_sm100_umma.hpp) without the lane-disable mask.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b16, uint32_t b_off, uint32_t b_lbo,
+                                            uint32_t b_sbo, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t b_lo = b16 + ((b_off >> 4) + (((b_lbo >> 4) & 0x3FFFu) << 16));
+    const uint32_t b_hi = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
