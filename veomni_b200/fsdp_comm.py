@@ -259,8 +259,12 @@ def _patch_copy_in() -> None:
         fc._div_if_needed = _div_if_needed
         # the all-gather copy-in is a registered op: override its CUDA kernel
         global _ag_lib, _orig_get_inputs
+        import warnings
+
         _ag_lib = torch.library.Library("fsdp", "IMPL")
-        _ag_lib.impl("all_gather_copy_in", _ag_copy_in, "CUDA", allow_override=True)
+        with warnings.catch_warnings():  # overriding a registered kernel is the point; torch warns about it once
+            warnings.simplefilter("ignore")
+            _ag_lib.impl("all_gather_copy_in", _ag_copy_in, "CUDA", allow_override=True)
         _orig_get_inputs = fc._get_param_all_gather_inputs
         fc._get_param_all_gather_inputs = _param_all_gather_inputs
 
