@@ -209,9 +209,10 @@ def test_attention_tcgen05_backward_matches_mma_full_size(cuda_dev):
         torch.testing.assert_close(a.float() / s, b.float() / s, atol=1e-2, rtol=2e-2, msg=lambda m, n=name: f"{n}: {m}")
 
 
-def test_attention_tcgen05_dq_operand_variants_agree(cuda_dev):
-    """The dQ kernel with Q / dO as TMEM-resident A operands (default) and the all-shared-memory-operand variant issue the
-    same MMAs on the same data: bit-identical dQ, on ragged lengths and at the Qwen3-8B size."""
+def test_attention_tcgen05_operand_variants_agree(cuda_dev):
+    """The backward kernels with their A operands in TMEM (default: Q / dO resident for dQ; P^T / dS^T for dK, dV) and the
+    all-shared-memory-operand variants issue the same MMAs on the same data: bit-identical gradients, on ragged lengths
+    and at the Qwen3-8B size."""
     from veomni_b200 import attention as A
 
     old = (A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS)
@@ -227,7 +228,8 @@ def test_attention_tcgen05_dq_operand_variants_agree(cuda_dev):
                 A.BWD_DQ_SS = ss
                 qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
                 A.flash_attn_varlen(qq, kk, vv, cu, max(lens)).backward(do)
-                grads[ss] = qq.grad
-            assert torch.equal(grads[False], grads[True]), lens
+                grads[ss] = (qq.grad, kk.grad, vv.grad)
+            for a, b in zip(grads[False], grads[True]):
+                assert torch.equal(a, b), lens
     finally:
         A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS = old

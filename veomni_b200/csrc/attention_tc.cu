@@ -559,10 +559,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
 }
 
-constexpr int TB_QS = 3;  // Q/dO smem ring depth of the dK/dV kernel
-enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = 4, K_STFULL = 7, K_STEMPTY = 9, K_PFULL = 11, K_PEMPTY = 13, K_DONE = 15,
-       K_COUNT = 16 };
+constexpr int TB_QS_SS = 3, TB_QS_TS = 5, TB_QS_MAX = 5;  // Q/dO smem ring depth of the dK/dV kernel
+enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = K_QFULL + TB_QS_MAX, K_STFULL = K_QEMPTY + TB_QS_MAX, K_STEMPTY = K_STFULL + 2,
+       K_PFULL = K_STEMPTY + 2, K_PEMPTY = K_PFULL + 2, K_DONE = K_PEMPTY + 2, K_COUNT = K_DONE + 1 };
 
+// TS = true: P^T and dS^T — the A operands of dV += P^T dO and dK += dS^T Q — are written by the softmax warps into
+// TMEM (tcgen05.st, two bf16 per column, over the S^T / dP^T buffer they were computed from) instead of shared memory.
+// ncu on the SS version: the shared-memory pipe is 83 % busy (tensor-core operand reads 56 %, P/dS stores + statistics
+// 27 %) with the tensor pipe at 50 %: ~270 KB cross it per 128x64 tile for 1024 clk of MMA. TS removes the 32 KB of
+// stores and the 32 KB of A reads per tile, the proxy fence, and frees 64 KB for a deeper Q/dO ring. No extra
+// synchronisation is needed for the aliasing: S^T_{j+2} is issued after dV/dK_j and tcgen05.mma executes in issue order.
+
+template <bool TS>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
@@ -570,11 +578,12 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sK = smem;                    // 32 KB
     uint8_t* sV = sK + TC_TILE;            // 32 KB
+    constexpr int TB_QS = TS ? TB_QS_TS : TB_QS_SS;
     uint8_t* sQ = sV + TC_TILE;            // TB_QS x 16 KB
     uint8_t* sdO = sQ + TB_QS * TB_SMALL;  // TB_QS x 16 KB
-    uint8_t* sPt = sdO + TB_QS * TB_SMALL; // 2 x 16 KB
-    uint8_t* sdSt = sPt + 2 * TB_DS;       // 2 x 16 KB
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sdSt + 2 * TB_DS);
+    uint8_t* sPt = sdO + TB_QS * TB_SMALL; // 2 x 16 KB (SS only)
+    uint8_t* sdSt = sPt + (TS ? 0 : 2 * TB_DS);       // 2 x 16 KB (SS only)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sdSt + (TS ? 0 : 2 * TB_DS));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + K_COUNT);
     float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2 stages][lse2 x64 | delta x64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -632,7 +641,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
                 const int qs = jb % TB_QS;                   // smem Q/dO stage
                 const uint32_t qph = (uint32_t)(jb / TB_QS) & 1u;
-                mbar_wait(&bar[K_STEMPTY + st], ph ^ 1);
+                if (!TS) mbar_wait(&bar[K_STEMPTY + st], ph ^ 1);  // TS: implied by PFULL_{jb-2} + in-order MMA execution
                 mbar_wait(&bar[K_QFULL + qs], qph);
                 tc_fence_after();
                 if (elect_one_sync()) {
@@ -664,13 +673,23 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                     const uint32_t pt_addr = smem_u32(sPt + st * TB_DS), dst_addr = smem_u32(sdSt + st * TB_DS);
                     const uint32_t q_addr = smem_u32(sQ + qs * TB_SMALL), do_addr = smem_u32(sdO + qs * TB_SMALL);
 #pragma unroll
-                    for (int k = 0; k < TB_N / 16; ++k)
-                        umma_f16_bo(tmem + 256, pt_addr >> 4, k * 32, 16, 1024, do_addr >> 4, k * 16 * 128, TB_N * 128, 1024,
-                                    idesc_acc, (i | k) ? 1u : 0u);
+                    for (int k = 0; k < TB_N / 16; ++k) {
+                        if (TS)  // A = P^T in TMEM over S^T[st]: 16 q (K) per step = 8 columns; q 32..63 start at column 32
+                            umma_f16_ts(tmem + 256, tmem + st * TB_N + (k >> 1) * 32 + (k & 1) * 8, do_addr >> 4, k * 16 * 128, TB_N * 128, 1024, idesc_acc,
+                                        (i | k) ? 1u : 0u);
+                        else
+                            umma_f16_bo(tmem + 256, pt_addr >> 4, k * 32, 16, 1024, do_addr >> 4, k * 16 * 128, TB_N * 128, 1024,
+                                        idesc_acc, (i | k) ? 1u : 0u);
+                    }
 #pragma unroll
-                    for (int k = 0; k < TB_N / 16; ++k)
-                        umma_f16_bo(tmem + 384, dst_addr >> 4, k * 32, 16, 1024, q_addr >> 4, k * 16 * 128, TB_N * 128, 1024,
-                                    idesc_acc, (i | k) ? 1u : 0u);
+                    for (int k = 0; k < TB_N / 16; ++k) {
+                        if (TS)
+                            umma_f16_ts(tmem + 384, tmem + 128 + st * TB_N + (k >> 1) * 32 + (k & 1) * 8, q_addr >> 4, k * 16 * 128, TB_N * 128, 1024, idesc_acc,
+                                        (i | k) ? 1u : 0u);
+                        else
+                            umma_f16_bo(tmem + 384, dst_addr >> 4, k * 32, 16, 1024, q_addr >> 4, k * 16 * 128, TB_N * 128, 1024,
+                                        idesc_acc, (i | k) ? 1u : 0u);
+                    }
                     umma_commit(&bar[K_QEMPTY + qs]);
                     umma_commit(&bar[K_PEMPTY + st]);
                     if (i == jobs - 1) umma_commit(&bar[K_DONE]);
@@ -712,7 +731,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             const float* dl_s = lse_s + 64;
             mbar_wait(&bar[K_STFULL + st], ph);
             tc_fence_after();
-            mbar_wait(&bar[K_PEMPTY + st], ph ^ 1);
+            if (!TS) mbar_wait(&bar[K_PEMPTY + st], ph ^ 1);
             const uint32_t pt_a = smem_u32(sPt + st * TB_DS), dst_a = smem_u32(sdSt + st * TB_DS);
             const bool need_mask = (qi * TB_N + TB_N > L) || (n0 + TC_BM > L) || (p.causal && n0 + TC_BM > qi * TB_N);
             {
@@ -721,9 +740,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
                 tmem_wait_ld();
-                tc_fence_before();  // early release of S^T/dP^T[st] (see the dQ kernel)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar[K_STEMPTY + st]);
+                if (!TS) {
+                    tc_fence_before();  // early release of S^T/dP^T[st] (see the dQ kernel)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar[K_STEMPTY + st]);
+                }
                 uint32_t pk[16], dk[16];
                 if (need_mask) {
 #pragma unroll
@@ -754,17 +775,25 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                         dk[(i >> 1) + 1] = f2_to_bf2(p2 * (__uint_as_float(dv[i + 2]) - d4.z), p3 * (__uint_as_float(dv[i + 3]) - d4.w));
                     }
                 }
+                if (TS) {
+                    // P^T / dS^T rows of this thread for q columns [c*32, c*32+32): 16 packed columns, written over the first
+                    // half of the 32 S^T / dP^T columns THIS warp just read (the other half-tile belongs to warp w+-4)
+                    tmem_st16(lane_base + st * TB_N + c * 32, pk);
+                    tmem_st16(lane_base + 128 + st * TB_N + c * 32, dk);
+                    tmem_wait_st();
+                } else {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const uint32_t a1 = swz_addr(pt_a, TC_BM, r, c * 4 + g), a2 = swz_addr(dst_a, TC_BM, r, c * 4 + g);
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
-                                 "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a2), "r"(dk[g * 4]), "r"(dk[g * 4 + 1]),
-                                 "r"(dk[g * 4 + 2]), "r"(dk[g * 4 + 3]) : "memory");
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t a1 = swz_addr(pt_a, TC_BM, r, c * 4 + g), a2 = swz_addr(dst_a, TC_BM, r, c * 4 + g);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                                     "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a2), "r"(dk[g * 4]), "r"(dk[g * 4 + 1]),
+                                     "r"(dk[g * 4 + 2]), "r"(dk[g * 4 + 3]) : "memory");
+                    }
                 }
             }
             tc_fence_before();
-            fence_async_smem();
+            if (!TS) fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar[K_PFULL + st]);
         }
@@ -877,12 +906,14 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     p.dout = (const __nv_bfloat16*)dout; p.do_st = st[6]; p.do_sh = st[7];
     const size_t smem_dq = 2 * TC_TILE + 2 * TB_KV_SS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
     const size_t smem_dq_ts = 2 * TB_KV_TS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
-    const size_t smem_kv = 2 * TC_TILE + 2 * TB_QS * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
+    const size_t smem_kv = 2 * TC_TILE + 2 * TB_QS_SS * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
+    const size_t smem_kv_ts = 2 * TC_TILE + 2 * TB_QS_TS * TB_SMALL + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
     static bool attr = false;
     if (!attr) {
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq_ts));
-        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
         attr = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -897,7 +928,8 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     }
     dim3 gk(p.tiles * k_heads * num_seqs);
     if (only != 1) {
-        attn_bwd_dkdv_tc_kernel<<<gk, 320, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+        if (ss_operands) attn_bwd_dkdv_tc_kernel<false><<<gk, 320, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+        else attn_bwd_dkdv_tc_kernel<true><<<gk, 320, smem_kv_ts, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
         vb200_count_launch(1);
     }
     VB_HOST_CHECK_LAUNCH();
