@@ -31,7 +31,7 @@ METRIC = "tokens/sec (Qwen3-8B FSDP2 bf16 seq4096)"
 
 
 # DRAM bytes per launch (read + write) of the three attention kernels at T=4096, 32/8 heads, D=128, from ncu --set full
-NCU_TRAFFIC_BYTES = {"bwd_dkdv": 86135808 + 4467712, "bwd_dq": 84984832 + 12128000, "fwd": 50374400 + 3454208}
+NCU_TRAFFIC_BYTES = {"bwd_dkdv": 86041088 + 4705024, "bwd_dq": 84966656 + 11869440, "fwd": 50374400 + 3454208}
 
 
 def _peaks():
@@ -279,7 +279,7 @@ def run_b200(args) -> None:
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16_tflops_sustained"], 4) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-                         # the same kernel at the same shape (profiles/r01_attn_bwd_*_tc_ncu.txt, r01_attn_fwd_tc_v3_ncu.txt)
+                         # the same kernel at the same shape (profiles/r01_attn_bwd_*_tc_ts_ncu.txt, r01_attn_fwd_tc_v3_ncu.txt)
                          "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r01_attn_*_ncu.txt (ncu --set full)",
                          "peak_source": f"{peaks['how']} (sustained cuBLAS bf16, kernel timed inside a long step)",
                          "avg_launch_ms": round(attn_avg_ms, 4), "launches_timed": len(attn_ms),

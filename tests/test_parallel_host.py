@@ -124,3 +124,42 @@ def test_pack_plan_reproduces_chunk_cat_layout():
                 r = el // chunk
                 out[r, off + el - r * chunk] = flat[el]
         assert torch.equal(out, ref), world
+
+
+def _fsdp_patch_worker(rank, world, path, outdir):
+    """FSDP2 on gloo/CPU with and without the copy-in patches installed: CPU tensors must take PyTorch's own path."""
+    import torch
+    import torch.distributed as dist
+    from torch.distributed.fsdp import MixedPrecisionPolicy, fully_shard
+
+    store = dist.FileStore(path, world)
+    dist.init_process_group("gloo", store=store, rank=rank, world_size=world)
+
+    def grads(patched: bool):
+        torch.manual_seed(5)
+        m = torch.nn.Sequential(torch.nn.Linear(24, 36, bias=False), torch.nn.Linear(36, 10))
+        mp_policy = MixedPrecisionPolicy(param_dtype=torch.bfloat16, reduce_dtype=torch.float32)
+        for layer in m:
+            fully_shard(layer, mp_policy=mp_policy)
+        fully_shard(m, mp_policy=mp_policy)
+        if patched:
+            from veomni_b200 import fsdp_comm
+
+            fsdp_comm._patch_copy_in()
+        x = torch.randn(8, 24, generator=torch.Generator().manual_seed(9 + rank))
+        m(x).float().square().mean().backward()
+        return [p.grad.to_local().clone() for p in m.parameters()]
+
+    a, b = grads(False), grads(True)
+    ok = all(torch.equal(x, y) for x, y in zip(a, b))
+    torch.save(ok, os.path.join(outdir, f"ok{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_copy_in_patches_leave_the_cpu_path_alone_world2_gloo():
+    import torch
+    import torch.multiprocessing as mp
+
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_fsdp_patch_worker, args=(2, os.path.join(d, "store"), d), nprocs=2, join=True)
+        assert all(torch.load(os.path.join(d, f"ok{r}.pt")) for r in range(2))
