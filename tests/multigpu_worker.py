@@ -396,6 +396,11 @@ def main():
     stage("allgather", test_barrier_and_allgather, symm, rank, world, dev)
     stage("reduce_scatter", test_reduce_scatter, symm, rank, world, dev)
     stage("reduce_scatter bf16 pull", test_reduce_scatter_bf16, symm, rank, world, dev)
+    # the world-size-generic kernel instantiation (what 8 GPUs run), forced on this group
+    os.environ["VB200_RS_GENERIC"] = "1"
+    stage("reduce_scatter (generic instantiation)", test_reduce_scatter, symm, rank, world, dev)
+    stage("reduce_scatter bf16 pull (generic instantiation)", test_reduce_scatter_bf16, symm, rank, world, dev)
+    os.environ.pop("VB200_RS_GENERIC")
     stage("ulysses", test_ulysses, rank, world, dev)
     stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
     stage("expert parallel dispatch/combine", test_ep, rank, world, dev)

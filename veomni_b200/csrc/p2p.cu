@@ -25,6 +25,8 @@
 // instead of hanging the GPU.
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vb {
@@ -583,7 +585,9 @@ extern "C" int vb200_reduce_scatter_f32(void* comm, int32_t channel, int64_t reg
         return vb200_set_error(VB200_EINVAL, "reduce_scatter: offset must be 256-byte aligned and inside the region");
     const int g = clamp_ctas(num_ctas);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (h->dev.world) {
+    // VB200_RS_GENERIC=1 forces the world-size-generic instantiation (the one 8 GPUs use) for testing on fewer GPUs
+    const char* gen = getenv("VB200_RS_GENERIC");
+    switch ((gen && gen[0] == '1') ? 0 : h->dev.world) {
         case 1: reduce_scatter_f32_kernel<1, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
         case 2: reduce_scatter_f32_kernel<2, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
         case 4: reduce_scatter_f32_kernel<4, 4><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
@@ -603,7 +607,9 @@ extern "C" int vb200_reduce_scatter_bf16(void* comm, int32_t channel, int64_t re
         return vb200_set_error(VB200_EINVAL, "reduce_scatter_bf16: offset must be 256-byte aligned and inside the region");
     const int g = clamp_ctas(num_ctas);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (h->dev.world) {
+    // VB200_RS_GENERIC=1 forces the world-size-generic instantiation (the one 8 GPUs use) for testing on fewer GPUs
+    const char* gen = getenv("VB200_RS_GENERIC");
+    switch ((gen && gen[0] == '1') ? 0 : h->dev.world) {
         case 1: reduce_scatter_bf16_kernel<1, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
         case 2: reduce_scatter_bf16_kernel<2, 8><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
         case 4: reduce_scatter_bf16_kernel<4, 4><<<g, 512, 0, st>>>(h->dev, channel, region_offset, chunk_elems, scale, out); break;
