@@ -84,7 +84,15 @@ def cpu_baseline(sample_tokens: int, iters: int, threads: int | None) -> dict:
 
     from oracle.qwen3_cpu import time_layer_step
 
-    cores = threads or os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
+    if threads:
+        cores = threads
+    else:
+        # all host threads are available to the reference arm, but small bf16 GEMMs stop scaling (and slow down) long
+        # before 128 threads: pick the fastest thread count on a 64-token probe and report the count actually used
+        cand = sorted({c for c in (ncpu, ncpu // 2, ncpu // 4, 32, 16) if 1 <= c <= ncpu})
+        probe = {c: time_layer_step(tokens=64, iters=1, threads=c) for c in cand}
+        cores = min(probe, key=probe.get)
     torch.set_num_threads(cores)
     t_layer = time_layer_step(tokens=sample_tokens, iters=iters, threads=cores)
     # 36 identical layers; per-token cost measured at `sample_tokens` (attention's quadratic term is
