@@ -215,21 +215,22 @@ def test_attention_tcgen05_operand_variants_agree(cuda_dev):
     and at the Qwen3-8B size."""
     from veomni_b200 import attention as A
 
-    old = (A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS)
+    old = (A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS, A.BWD_PP)
     try:
         A.FWD_IMPL = A.BWD_IMPL = "tc"
-        for lens, Hq, Hk in (([1, 63, 64, 65, 127, 129, 300], 4, 2), ([4096], 32, 8)):
+        for lens, Hq, Hk in (([1, 63, 64, 65, 127, 129, 300], 4, 2), ([700, 64], 6, 1), ([4096], 32, 8)):
             T = sum(lens)
             g = torch.Generator().manual_seed(T)
             q, k, v, do = (torch.randn(T, h, 128, generator=g).to(BF).to(cuda_dev) for h in (Hq, Hk, Hk, Hq))
             cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
             grads = {}
-            for ss in (False, True):
-                A.BWD_DQ_SS = ss
+            for variant in ("tmem", "smem", "pingpong"):
+                A.BWD_DQ_SS, A.BWD_PP = variant == "smem", variant == "pingpong"
                 qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
                 A.flash_attn_varlen(qq, kk, vv, cu, max(lens)).backward(do)
-                grads[ss] = (qq.grad, kk.grad, vv.grad)
-            for a, b in zip(grads[False], grads[True]):
-                assert torch.equal(a, b), lens
+                grads[variant] = (qq.grad, kk.grad, vv.grad)
+            for variant in ("smem", "pingpong"):
+                for a, b in zip(grads["tmem"], grads[variant]):
+                    assert torch.equal(a, b), (variant, lens)
     finally:
-        A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS = old
+        A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS, A.BWD_PP = old

@@ -42,6 +42,12 @@ def bench_attention(dev, iters):
         report("attn_fwd+bwd_tcgen05[4096,32/8,128,causal]", time_fn(fb, gsets, iters), flops=flops_fwd * 3.5)
     except Exception as ex:  # noqa: BLE001
         print({"attn_bwd_tcgen05": str(ex)})
+    try:
+        A.BWD_PP = not A.BWD_PP
+        report(f"attn_fwd+bwd_tcgen05 (BWD_PP={A.BWD_PP})[4096,32/8,128,causal]", time_fn(fb, gsets, iters), flops=flops_fwd * 3.5)
+    except Exception as ex:  # noqa: BLE001
+        print({"attn_bwd_tcgen05_pp": str(ex)})
+    A.BWD_PP = not A.BWD_PP
     A.FWD_IMPL, A.BWD_IMPL = old2
     try:
         from flash_attn import flash_attn_varlen_func

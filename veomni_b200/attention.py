@@ -41,6 +41,7 @@ def _prof_end(h):
 # Forward implementation for head_dim 128: "tc" = tcgen05/TMEM pipeline (attention_tc.cu), "mma" = mma.sync kernel.
 FWD_IMPL = os.environ.get("VB200_ATTN_FWD", "tc")
 BWD_IMPL = os.environ.get("VB200_ATTN_BWD", "tc")
+BWD_PP = os.environ.get("VB200_ATTN_BWD_PP", "0") == "1"  # softmax warpgroups on alternate tiles ("ping-pong")
 BWD_DQ_SS = False  # True: dQ kernel with every MMA operand in shared memory (cross-check of the A-in-TMEM default)
 
 
@@ -118,7 +119,7 @@ class _VarlenAttn(torch.autograd.Function):
                     check(lib.vb200_attn_varlen_bwd_tc(q.data_ptr(), k.data_ptr(), v.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                                        delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
                                                        cu.data_ptr(), cu.numel() - 1, max_seqlen, T, Hq, Hk, D, strides, scale,
-                                                       (1 if causal else 0) | (only << 8) | ((1 << 10) if BWD_DQ_SS else 0),
+                                                       (1 if causal else 0) | (only << 8) | ((1 << 10) if BWD_DQ_SS else 0) | ((1 << 11) if BWD_PP else 0),
                                                        stream_ptr()),
                           "vb200_attn_varlen_bwd_tc")
                     _prof_end(hprof)

@@ -321,7 +321,10 @@ enum { Q_LOAD = 0, Q_KFULL = 1, Q_VFULL = Q_KFULL + TB_KV_MAX, Q_KEMPTY = Q_VFUL
 // shared memory. The SS version moves ~176 KB through shared memory per 128x64 tile (A re-read for every tile) for
 // 768 clk of MMA and is bound by the 128 B/clk shared-memory pipe (ncu: 57 % of it with the tensor pipe at 37 %);
 // with A in TMEM it is ~112 KB and the N=64 MMAs run at their 32-clk floor instead of 48.
-template <bool TS>
+// PP = true ("ping-pong"): the two softmax warpgroups (warps 2-5 / 6-9) take alternate K/V tiles — each thread does
+// all 64 columns of its row for its tiles and owns one S/dP buffer — instead of all eight warps splitting the columns
+// of the same tile and then waiting together for the next S: while one warpgroup waits for its MMAs the other computes.
+template <bool TS, bool PP>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -350,7 +353,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (int i = 0; i < Q_COUNT; ++i) {
             const bool by_warps = (i >= Q_SEMPTY && i < Q_SEMPTY + 2) || (i >= Q_DSFULL && i < Q_DSFULL + 2) ||
                                   (TS && i == Q_LOAD);
-            mbar_init(&bar[i], by_warps ? 8 : 1);
+            mbar_init(&bar[i], by_warps ? ((PP && i != Q_LOAD) ? 4 : 8) : 1);
         }
         mbar_fence_init();
     }
@@ -479,7 +482,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar[Q_LOAD]);
         }
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = PP ? cw : 0; j < n_tiles; j += PP ? 2 : 1) {
             const int st = j & 1;
             const uint32_t ph = (uint32_t)(j >> 1) & 1u;
             mbar_wait(&bar[Q_SPFULL + st], ph);
@@ -488,17 +491,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const uint32_t ds_a = smem_u32(sdS + st * TB_DS);
             // tiles fully below the diagonal and inside the sequence need no per-element predicate
             const bool need_mask = (j * TB_N + TB_N > L) || (m0 + TC_BM > L) || (p.causal && j * TB_N + TB_N > m0);
-            {
-                const int c = cw;
+#pragma unroll 1
+            for (int c = PP ? 0 : cw; c < (PP ? 2 : cw + 1); ++c) {
                 uint32_t sv[32], dv[32];
                 tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
                 tmem_wait_ld();
                 // S/dP[st] are in registers: release the TMEM buffer now so the MMA warp can run S/dP of tile j+2
                 // while this tile's exponentials are still being computed
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar[Q_SEMPTY + st]);
+                if (!PP || c == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar[Q_SEMPTY + st]);
+                }
                 uint32_t pk[16];
                 if (need_mask) {
 #pragma unroll
@@ -570,7 +575,7 @@ enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = K_QFULL + TB_QS_MAX, K_STFULL = K_QEM
 // stores and the 32 KB of A reads per tile, the proxy fence, and frees 64 KB for a deeper Q/dO ring. No extra
 // synchronisation is needed for the aliasing: S^T_{j+2} is issued after dV/dK_j and tcgen05.mma executes in issue order.
 
-template <bool TS>
+template <bool TS, bool PP>  // PP: the two softmax warpgroups take alternate (head, q tile) jobs, see the dQ kernel
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
@@ -585,7 +590,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     uint8_t* sdSt = sPt + (TS ? 0 : 2 * TB_DS);       // 2 x 16 KB (SS only)
     uint64_t* bar = reinterpret_cast<uint64_t*>(sdSt + (TS ? 0 : 2 * TB_DS));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + K_COUNT);
-    float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2 stages][lse2 x64 | delta x64]
+    float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2 stages (PP: 2 warpgroups x 2)][lse2 x64 | delta x64]
+    static_assert(!PP || TS, "the ping-pong variant is built on the TMEM-operand kernel");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int order, hk, seq;
     tile_of_block(p.Hk, p.nseq, order, hk, seq);
@@ -600,7 +606,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     if (threadIdx.x == 0) {
         for (int i = 0; i < K_COUNT; ++i) {
             const bool by_warps = (i >= K_STEMPTY && i < K_STEMPTY + 2) || (i >= K_PFULL && i < K_PFULL + 2);
-            mbar_init(&bar[i], by_warps ? 8 : 1);
+            mbar_init(&bar[i], by_warps ? (PP ? 4 : 8) : 1);
         }
         mbar_fence_init();
     }
@@ -702,7 +708,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         const int q = warp & 3;
         const int cw = (warp - 2) >> 2;
         const int r = q * 32 + lane;
-        const int tid = (warp - 2) * 32 + lane;  // 0..255 over the softmax warps
+        const int tid = PP ? ((warp - 2) & 3) * 32 + lane   // 0..127 inside this warpgroup
+                           : (warp - 2) * 32 + lane;       // 0..255 over the softmax warps
         const int n = n0 + r;  // kv index of this thread's row
         // per-column statistics of the first job are fetched up front; each later job's are prefetched one job ahead
         auto load_stat = [&](int jb) -> float {
@@ -716,26 +723,29 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             }
             return p.delta[(int64_t)hh * p.total + s0 + mm];
         };
-        float stat_next = load_stat(0);
+        float stat_next = load_stat(PP ? cw : 0);
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         const float sl2 = p.scale * kLog2eTc;
-        for (int jb = 0; jb < jobs; ++jb) {
+        for (int jb = PP ? cw : 0; jb < jobs; jb += PP ? 2 : 1) {
             const int st = jb & 1;
             const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
             const int qi = i_start + jb % nq;
             // per-column (q index) softmax statistics of this q tile: 64 lse2 + 64 delta values through smem
-            if (tid < 128) (sStat + st * 128)[tid] = stat_next;
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps only
-            stat_next = load_stat(jb + 1);
-            const float* lse_s = sStat + st * 128;
+            // (PP: a strip pair per warpgroup, alternating with the warpgroup's job count)
+            float* strip = sStat + (PP ? (cw * 2 + (int)ph) : st) * 128;
+            if (tid < 128) strip[tid] = stat_next;
+            if (PP) asm volatile("bar.sync %0, 128;" ::"r"(1 + cw) : "memory");  // this warpgroup only
+            else asm volatile("bar.sync 1, 256;" ::: "memory");                  // the 8 softmax warps only
+            stat_next = load_stat(jb + (PP ? 2 : 1));
+            const float* lse_s = strip;
             const float* dl_s = lse_s + 64;
             mbar_wait(&bar[K_STFULL + st], ph);
             tc_fence_after();
             if (!TS) mbar_wait(&bar[K_PEMPTY + st], ph ^ 1);
             const uint32_t pt_a = smem_u32(sPt + st * TB_DS), dst_a = smem_u32(sdSt + st * TB_DS);
             const bool need_mask = (qi * TB_N + TB_N > L) || (n0 + TC_BM > L) || (p.causal && n0 + TC_BM > qi * TB_N);
-            {
-                const int c = cw;
+#pragma unroll 1
+            for (int c = PP ? 0 : cw; c < (PP ? 2 : cw + 1); ++c) {
                 uint32_t sv[32], dv[32];
                 tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
@@ -880,6 +890,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     // dQ / only the dK-dV kernel (used to time the two kernels separately; 0 = both); bit 10 = SS-operand dQ kernel.
     const int only = (causal >> 8) & 3;
     const bool ss_operands = (causal >> 10) & 1;  // bit 10: all MMA operands from shared memory (cross-check variant)
+    const bool pingpong = (causal >> 11) & 1;     // bit 11: softmax warpgroups on alternate tiles
     causal &= 1;
     if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: head_dim must be 128");
     if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: Hq % Hk != 0");
@@ -907,13 +918,15 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     const size_t smem_dq = 2 * TC_TILE + 2 * TB_KV_SS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
     const size_t smem_dq_ts = 2 * TB_KV_TS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
     const size_t smem_kv = 2 * TC_TILE + 2 * TB_QS_SS * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
-    const size_t smem_kv_ts = 2 * TC_TILE + 2 * TB_QS_TS * TB_SMALL + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
+    const size_t smem_kv_ts = 2 * TC_TILE + 2 * TB_QS_TS * TB_SMALL + K_COUNT * 8 + 16 + 4 * 128 * 4 + 64;
     static bool attr = false;
     if (!attr) {
-        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
-        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq_ts));
-        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
-        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq_ts));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq_ts));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
         attr = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -921,15 +934,17 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     p.nseq = num_seqs;
     dim3 gq(p.tiles * q_heads * num_seqs);
     if (only != 2) {
-        if (ss_operands) attn_bwd_dq_tc_kernel<false><<<gq, 320, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
-        else attn_bwd_dq_tc_kernel<true><<<gq, 320, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        if (ss_operands) attn_bwd_dq_tc_kernel<false, false><<<gq, 320, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        else if (pingpong) attn_bwd_dq_tc_kernel<true, true><<<gq, 320, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        else attn_bwd_dq_tc_kernel<true, false><<<gq, 320, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         vb200_count_launch(1);
         VB_HOST_CHECK_LAUNCH();
     }
     dim3 gk(p.tiles * k_heads * num_seqs);
     if (only != 1) {
-        if (ss_operands) attn_bwd_dkdv_tc_kernel<false><<<gk, 320, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
-        else attn_bwd_dkdv_tc_kernel<true><<<gk, 320, smem_kv_ts, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+        if (ss_operands) attn_bwd_dkdv_tc_kernel<false, false><<<gk, 320, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+        else if (pingpong) attn_bwd_dkdv_tc_kernel<true, true><<<gk, 320, smem_kv_ts, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+        else attn_bwd_dkdv_tc_kernel<true, false><<<gk, 320, smem_kv_ts, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
         vb200_count_launch(1);
     }
     VB_HOST_CHECK_LAUNCH();
