@@ -516,11 +516,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         pk[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(dv[i]) - dl), p1 * (__uint_as_float(dv[i + 1]) - dl));
                     }
                 } else {
+                    const float2 sl2v = make_float2(sl2, sl2), nlse = make_float2(-lse2, -lse2), ndl = make_float2(-dl, -dl);
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = exp2f(__uint_as_float(sv[i]) * sl2 - lse2);
-                        const float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse2);
-                        pk[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(dv[i]) - dl), p1 * (__uint_as_float(dv[i + 1]) - dl));
+                    for (int i = 0; i < 32; i += 2) {  // packed pairs: FFMA2, 2x MUFU, FADD2, FMUL2, F2FP
+                        const float2 t = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, nlse);
+                        const float2 u = fadd2(make_float2(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), ndl);
+                        const float2 w = fmul2(make_float2(exp2f(t.x), exp2f(t.y)), u);
+                        pk[i >> 1] = f2_to_bf2(w.x, w.y);
                     }
                 }
 #pragma unroll
@@ -717,11 +719,12 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             const int hh = hk * G + jb / nq, qi = i_start + jb % nq;
             const int mm = qi * TB_N + (tid & 63);
             if (mm >= L) return 0.f;
+            // stored negated: the strip holds -lse*log2(e) and -delta so the packed FMA / ADD take them as addends
             if (tid < 64) {
                 const float l = p.lse[(int64_t)hh * p.total + s0 + mm];
-                return (l == -INFINITY) ? 0.f : l * kLog2eTc;
+                return (l == -INFINITY) ? 0.f : -l * kLog2eTc;
             }
-            return p.delta[(int64_t)hh * p.total + s0 + mm];
+            return -p.delta[(int64_t)hh * p.total + s0 + mm];
         };
         float stat_next = load_stat(PP ? cw : 0);
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
@@ -764,8 +767,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                         for (int e = 0; e < 2; ++e) {
                             const int m = qi * TB_N + c * 32 + i + e;  // q index (column)
                             const bool ok = n < L && m < L && (!p.causal || n <= m);
-                            pe[e] = ok ? exp2f(__uint_as_float(sv[i + e]) * sl2 - lse_s[c * 32 + i + e]) : 0.f;
-                            de[e] = pe[e] * (__uint_as_float(dv[i + e]) - dl_s[c * 32 + i + e]);
+                            pe[e] = ok ? exp2f(__uint_as_float(sv[i + e]) * sl2 + lse_s[c * 32 + i + e]) : 0.f;
+                            de[e] = pe[e] * (__uint_as_float(dv[i + e]) + dl_s[c * 32 + i + e]);
                         }
                         pk[i >> 1] = f2_to_bf2(pe[0], pe[1]);
                         dk[i >> 1] = f2_to_bf2(de[0], de[1]);
@@ -773,16 +776,19 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c * 32 + i);
-                        const float4 d4 = *reinterpret_cast<const float4*>(dl_s + c * 32 + i);
-                        const float p0 = exp2f(__uint_as_float(sv[i + 0]) * sl2 - l4.x);
-                        const float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - l4.y);
-                        const float p2 = exp2f(__uint_as_float(sv[i + 2]) * sl2 - l4.z);
-                        const float p3 = exp2f(__uint_as_float(sv[i + 3]) * sl2 - l4.w);
-                        pk[i >> 1] = f2_to_bf2(p0, p1);
-                        pk[(i >> 1) + 1] = f2_to_bf2(p2, p3);
-                        dk[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(dv[i + 0]) - d4.x), p1 * (__uint_as_float(dv[i + 1]) - d4.y));
-                        dk[(i >> 1) + 1] = f2_to_bf2(p2 * (__uint_as_float(dv[i + 2]) - d4.z), p3 * (__uint_as_float(dv[i + 3]) - d4.w));
+                        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c * 32 + i);  // -lse2 of 4 q columns
+                        const float4 d4 = *reinterpret_cast<const float4*>(dl_s + c * 32 + i);   // -delta
+                        const float2 sl2v = make_float2(sl2, sl2);
+                        const float2 t0 = ffma2(make_float2(__uint_as_float(sv[i + 0]), __uint_as_float(sv[i + 1])), sl2v, make_float2(l4.x, l4.y));
+                        const float2 t1 = ffma2(make_float2(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2v, make_float2(l4.z, l4.w));
+                        const float2 e0 = make_float2(exp2f(t0.x), exp2f(t0.y)), e1 = make_float2(exp2f(t1.x), exp2f(t1.y));
+                        const float2 u0 = fadd2(make_float2(__uint_as_float(dv[i + 0]), __uint_as_float(dv[i + 1])), make_float2(d4.x, d4.y));
+                        const float2 u1 = fadd2(make_float2(__uint_as_float(dv[i + 2]), __uint_as_float(dv[i + 3])), make_float2(d4.z, d4.w));
+                        const float2 w0 = fmul2(e0, u0), w1 = fmul2(e1, u1);
+                        pk[i >> 1] = f2_to_bf2(e0.x, e0.y);
+                        pk[(i >> 1) + 1] = f2_to_bf2(e1.x, e1.y);
+                        dk[i >> 1] = f2_to_bf2(w0.x, w0.y);
+                        dk[(i >> 1) + 1] = f2_to_bf2(w1.x, w1.y);
                     }
                 }
                 if (TS) {
