@@ -72,3 +72,13 @@ def fused_linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, label
         dh[r0:r1] = g @ weight
         dw += g.t() @ hidden[r0:r1]
     return total * scale, dh, dw
+
+
+def reduce_sequence_parallel_loss(losses: list[float], n_valid: list[int], upstream: float = 1.0):
+    """``reduce_sequence_parallel_loss`` / ``ReduceLoss`` (veomni/distributed/sequence_parallel/loss.py:27-64) over the
+    ranks of one SP group: forward sum_r(loss_r * n_r) / max(sum_r n_r, 1) with ranks that hold no valid token
+    contributing 0; backward d/d loss_r = world * n_r * upstream / max(sum n, 1). Returns (reduced, [grad per rank])."""
+    world = len(losses)
+    total = sum((l if n > 0 else 0.0) * n for l, n in zip(losses, n_valid))
+    denom = max(sum(n_valid), 1)
+    return total / denom, [world * n * upstream / denom for n in n_valid]

@@ -238,6 +238,18 @@ def _worker(rank, world, path, outdir):
     model(xin).square().sum().backward()
     res["fsdp"] = {"full_params": full, "x": xin,
                    "sharded_grads": {n: p.grad.to_local().clone() for n, p in model.named_parameters()}}
+    # ---- SP loss reduction (reference): token-weighted mean over the SP group + its backward ----
+    from veomni.distributed.sequence_parallel import comm as SPC
+    from veomni.distributed.sequence_parallel.loss import reduce_sequence_parallel_loss
+
+    SPC.set_unified_sequence_parallel_group(group)
+    cases = []
+    for loss_v, n_valid in ((1.5 + rank, 7 + 3 * rank), (0.25, 0 if rank == 0 else 5), (2.0, 0)):
+        loss_in = torch.tensor(float(loss_v), requires_grad=True)
+        out = reduce_sequence_parallel_loss(loss_in * 1.0, torch.tensor(n_valid))
+        (g_in,) = torch.autograd.grad(out * 3.0, loss_in)
+        cases.append({"loss": float(loss_v), "n_valid": n_valid, "reduced": out.detach().clone(), "grad": g_in.clone()})
+    res["sp_loss"] = cases
     torch.save(res, os.path.join(outdir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -292,6 +304,14 @@ def gen_multirank():
             eq(shards[r].view(ref.shape), ref, f"fsdp2 reduce-scatter {name} rank{r}")
         ag = o_comm.fsdp_all_gather([c.reshape(-1) for c in full[name].chunk(world, dim=0)], torch.bfloat16)
         eq(ag.view(full[name].shape), full[name].to(torch.bfloat16), f"fsdp2 all-gather {name}")
+    # SP loss reduction: oracle vs reference (forward value and the gradient of 3 * reduced w.r.t. each rank's loss)
+    for c in range(len(ranks[0]["sp_loss"])):
+        red, grads_sp = o_loss.reduce_sequence_parallel_loss([ranks[r]["sp_loss"][c]["loss"] for r in range(world)],
+                                                             [ranks[r]["sp_loss"][c]["n_valid"] for r in range(world)], 3.0)
+        for r in range(world):
+            eq(torch.tensor(red), ranks[r]["sp_loss"][c]["reduced"], f"sp loss reduce case{c} rank{r}", atol=1e-6, rtol=1e-6)
+            eq(torch.tensor(grads_sp[r]), ranks[r]["sp_loss"][c]["grad"], f"sp loss grad case{c} rank{r}", atol=1e-6, rtol=1e-6)
+
     for r in ranks:
         r["fsdp"]["bf16_grads"] = None
     for r in range(world):

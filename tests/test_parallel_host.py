@@ -163,3 +163,33 @@ def test_copy_in_patches_leave_the_cpu_path_alone_world2_gloo():
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_fsdp_patch_worker, args=(2, os.path.join(d, "store"), d), nprocs=2, join=True)
         assert all(torch.load(os.path.join(d, f"ok{r}.pt")) for r in range(2))
+
+
+def _sp_loss_worker(rank, world, path, outdir):
+    import torch
+    import torch.distributed as dist
+
+    from veomni_b200.cross_entropy import _ReduceLoss
+
+    store = dist.FileStore(path, world)
+    dist.init_process_group("gloo", store=store, rank=rank, world_size=world)
+    f = torch.load(os.path.join(os.path.dirname(__file__), "golden", "multirank.pt"), weights_only=False)["ranks"][rank]["sp_loss"]
+    ok = True
+    for case in f:
+        loss_in = torch.tensor(case["loss"], requires_grad=True)
+        out = _ReduceLoss.apply(loss_in * 1.0, torch.tensor(case["n_valid"]), dist.group.WORLD)
+        (g,) = torch.autograd.grad(out * 3.0, loss_in)
+        ok = ok and torch.allclose(out.detach(), case["reduced"], atol=1e-6) and torch.allclose(g, case["grad"], atol=1e-6)
+    torch.save(ok, os.path.join(outdir, f"ok{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_sp_loss_reduce_matches_reference_world2_gloo():
+    """The SP loss reduction of the causal-LM loss wrapper against the reference's ReduceLoss outputs (fixture made by the
+    reference on a 2-rank gloo group): token-weighted mean, empty ranks, all-empty group, and the backward factor."""
+    import torch
+    import torch.multiprocessing as mp
+
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_sp_loss_worker, args=(2, os.path.join(d, "store"), d), nprocs=2, join=True)
+        assert all(torch.load(os.path.join(d, f"ok{r}.pt")) for r in range(2))
