@@ -7,6 +7,8 @@ tests/models/test_models_patch.py:327-329; SP attention 2e-3 on grads of fp32 SD
 """
 import math
 
+import os
+
 import pytest
 import torch
 
@@ -234,3 +236,31 @@ def test_attention_tcgen05_operand_variants_agree(cuda_dev):
                     assert torch.equal(a, b), (variant, lens)
     finally:
         A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS, A.BWD_PP = old
+
+
+@pytest.mark.skipif(os.environ.get("VB200_EXPERIMENTAL", "0") != "1", reason="experimental kernel variant: set VB200_EXPERIMENTAL=1")
+def test_attention_tcgen05_forward_eight_softmax_warps(cuda_dev):
+    """attn_fwd_tc_kernel<W8> (two warps per row, half the columns each) against the default four-warp kernel: the row
+    maxima, the lazy-rescale decisions and every exponential are the same numbers, only the row sums are added in a
+    different order -> outputs within 1 bf16 ulp, lse within 1e-5; plus the oracle parity of the ragged cases."""
+    from veomni_b200 import attention as A
+
+    old = (A.FWD_IMPL, A.FWD_W8)
+    try:
+        A.FWD_IMPL = "tc"
+        for lens, Hq, Hk, causal in (([1, 63, 64, 65, 127, 129, 300], 4, 2, True), ([200, 333], 8, 2, False), ([4096], 32, 8, True)):
+            T = sum(lens)
+            g = torch.Generator().manual_seed(T + 1)
+            q, k, v = (torch.randn(T, h, 128, generator=g).to(BF).to(cuda_dev) for h in (Hq, Hk, Hk))
+            cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
+            outs = {}
+            for w8 in (False, True):
+                A.FWD_W8 = w8
+                with torch.no_grad():
+                    outs[w8] = A.flash_attn_varlen(q, k, v, cu, max(lens), causal=causal, return_lse=True)
+            torch.testing.assert_close(outs[True][0].float(), outs[False][0].float(), atol=1e-2, rtol=8e-3)
+            torch.testing.assert_close(outs[True][1], outs[False][1], atol=1e-5, rtol=1e-5)
+        A.FWD_W8 = True
+        _run(cuda_dev, [1, 63, 64, 65, 127, 129, 300], Hq=4, Hk=2, D=128, seed=99)
+    finally:
+        A.FWD_IMPL, A.FWD_W8 = old

@@ -1,4 +1,6 @@
 """Additional microbenchmarks (attention, comm, MoE); imported lazily by tools/microbench.py."""
+import os
+
 import torch
 
 from tools.microbench import BF, report, time_fn
@@ -26,6 +28,15 @@ def bench_attention(dev, iters):
                    flops=flops_fwd)
     except Exception as ex:  # noqa: BLE001
         print({"attn_fwd_tcgen05": str(ex)})
+    if os.environ.get("VB200_EXPERIMENTAL", "0") == "1":
+        A.FWD_IMPL, A.FWD_W8 = "tc", True
+        try:
+            with torch.no_grad():
+                report("attn_fwd_tcgen05 (8 softmax warps, experimental)[4096,32/8,128,causal]",
+                       time_fn(lambda q, k, v: flash_attn_varlen(q, k, v, cu, T), sets, iters), flops=flops_fwd)
+        except Exception as ex:  # noqa: BLE001
+            print({"attn_fwd_tcgen05_w8": str(ex)})
+        A.FWD_W8 = False
     A.FWD_IMPL = old
     gsets = [tuple(t.clone().requires_grad_(True) for t in s) for s in sets]
     do = torch.randn(T, Hq, D, device=dev, dtype=BF)

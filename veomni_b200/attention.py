@@ -41,6 +41,8 @@ def _prof_end(h):
 # Forward implementation for head_dim 128: "tc" = tcgen05/TMEM pipeline (attention_tc.cu), "mma" = mma.sync kernel.
 FWD_IMPL = os.environ.get("VB200_ATTN_FWD", "tc")
 BWD_IMPL = os.environ.get("VB200_ATTN_BWD", "tc")
+# EXPERIMENTAL (not yet run on hardware): eight softmax warps in the tcgen05 forward, see attn_fwd_tc_kernel<W8>
+FWD_W8 = os.environ.get("VB200_ATTN_FWD_W8", "0") == "1"
 BWD_PP = os.environ.get("VB200_ATTN_BWD_PP", "0") == "1"  # softmax warpgroups on alternate tiles ("ping-pong")
 BWD_DQ_SS = False  # True: dQ kernel with every MMA operand in shared memory (cross-check of the A-in-TMEM default)
 
@@ -85,10 +87,12 @@ class _VarlenAttn(torch.autograd.Function):
         lib = _lib.load()
         with torch.cuda.device(q.device):
             hprof = _prof("fwd")
-            fwd = lib.vb200_attn_varlen_fwd_tc if (FWD_IMPL == "tc" and D == 128) else lib.vb200_attn_varlen_fwd
+            use_tc = FWD_IMPL == "tc" and D == 128
+            fwd = lib.vb200_attn_varlen_fwd_tc if use_tc else lib.vb200_attn_varlen_fwd
+            flags = (1 if causal else 0) | ((1 << 8) if (use_tc and FWD_W8) else 0)
             check(
                 fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(), cu.data_ptr(), nseq,
-                    int(max_seqlen), T, Hq, Hk, D, _strides(q, k, v, o), scale, 1 if causal else 0, stream_ptr()),
+                    int(max_seqlen), T, Hq, Hk, D, _strides(q, k, v, o), scale, flags, stream_ptr()),
                 "vb200_attn_varlen_fwd",
             )
             _prof_end(hprof)

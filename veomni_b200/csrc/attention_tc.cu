@@ -46,12 +46,13 @@ constexpr int TC_TILE = TC_BM * TC_D * 2;  // 32 KB
 constexpr int TC_VSTAGES = 3;              // V is held until PV_j retires (one tile later than K): deeper ring
 constexpr float kLog2eTc = 1.4426950408889634f;
 
-// Row max of a 128-column S tile held in registers; MASK applies the causal / sequence-end mask in place.
-template <bool MASK>
-__device__ __forceinline__ float tile_row_max(uint32_t (&sv)[4][32], int n0, int m, int L, int causal) {
+// Row max of NC 32-column chunks of an S tile held in registers (first column n0); MASK applies the causal /
+// sequence-end mask in place.
+template <bool MASK, int NC>
+__device__ __forceinline__ float tile_row_max(uint32_t (&sv)[NC][32], int n0, int m, int L, int causal) {
     float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < NC; ++c) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             if (MASK) {
@@ -73,9 +74,18 @@ enum {  // barrier indices
 // into it), S is read from TMEM exactly once per tile, and the running max used in the exponentials is only
 // refreshed — with a TMEM read-modify-write of O — when a row's new max exceeds it by more than 2^8
 // ("lazy rescale"); TMEM read bandwidth, not the tensor pipe, is the scarce resource in this kernel.
-__global__ void __launch_bounds__(192, 1)
+//
+// W8 = true: eight softmax warps instead of four — warps w and w+4 share a TMEM lane quadrant (a row) and take the
+// left / right 64 columns of every S tile; the two half-row maxima are exchanged through shared memory (one named
+// barrier per tile), each thread keeps the partial row sum of its columns and rescales / writes its half of O.
+// Motivation (tools/ubench_sm100.cu, profiles/r01_ubench_sm100.jsonl): with four warps `tcgen05.ld` delivers 88 B/clk
+// and MUFU.EX2 11.9 lanes/clk per SM — 740 + 1377 clk of the 2800 clk a 128x128 tile takes — against 155 B/clk and
+// 16 lanes/clk with eight.  EXPERIMENTAL until validated on hardware (attention.FWD_W8, default off).
+template <bool W8>
+__global__ void __launch_bounds__(W8 ? 320 : 192, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+    constexpr int NC = W8 ? 2 : 4;  // 32-column chunks of S per thread
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TC_TILE;          // 2 stages
@@ -83,6 +93,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint8_t* sP = sV + TC_VSTAGES * TC_TILE;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sP + TC_TILE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
+    float* sHalf = reinterpret_cast<float*>(tmem_slot + 4);  // W8: [2 tile parities][2 halves][128 rows] half-row maxima / sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     int order, h, seq;
@@ -98,7 +109,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < B_COUNT; ++i) {
             const bool by_warps = (i >= B_SEMPTY && i < B_SEMPTY + 2) || i == B_PFULL;
-            mbar_init(&bar[i], by_warps ? 4 : 1);
+            mbar_init(&bar[i], by_warps ? (W8 ? 8 : 4) : 1);
         }
         mbar_fence_init();
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -178,8 +189,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
         }
     } else {
-        // ===== softmax: thread == query row =====
+        // ===== softmax: thread == query row (W8: one half of its columns) =====
         const int q = warp & 3;
+        const int cw = W8 ? (warp - 2) >> 2 : 0;  // column half of this warp
         const int r = q * 32 + lane;
         const int m = m0 + r;  // sequence-relative query index
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
@@ -191,17 +203,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t ph = (uint32_t)(j >> 1) & 1u;
             mbar_wait(&bar[B_SFULL + st], ph);
             tc_fence_after();
-            uint32_t sv[4][32];
+            uint32_t sv[NC][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32_nowait(lane_base + st * TC_BN + c * 32, sv[c]);
+            for (int c = 0; c < NC; ++c) tmem_ld32_nowait(lane_base + st * TC_BN + (cw * NC + c) * 32, sv[c]);
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar[B_SEMPTY + st]);  // S[st] is in registers: the next QK^T may overwrite it
 
             const bool need_mask = (j * TC_BN + TC_BN > L) || (p.causal && j * TC_BN + TC_BN > m0);
-            const float mx = need_mask ? tile_row_max<true>(sv, j * TC_BN, m, L, p.causal)
-                                       : tile_row_max<false>(sv, j * TC_BN, m, L, p.causal);
+            const int nfirst = j * TC_BN + cw * NC * 32;
+            float mx = need_mask ? tile_row_max<true, NC>(sv, nfirst, m, L, p.causal)
+                                 : tile_row_max<false, NC>(sv, nfirst, m, L, p.causal);
+            if (W8) {  // the row's maximum over both halves
+                float* slot = sHalf + (j & 1) * 256;
+                slot[cw * 128 + r] = mx;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                mx = fmaxf(mx, slot[(cw ^ 1) * 128 + r]);
+            }
             // lazy rescale: refresh m_ref only when this tile exceeds it by more than 2^8 (or on the first tile)
             float alpha = 1.f;
             bool refresh = false;
@@ -214,15 +233,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             // P buffer free <=> PV_{j-1} committed; the same barrier also means O holds tiles 0..j-1
             if (j >= 1) mbar_wait(&bar[B_PVDONE], (uint32_t)(j - 1) & 1u);
-            if (__any_sync(0xffffffffu, refresh)) {  // warp-collective TMEM read-modify-write of O
+            if (__any_sync(0xffffffffu, refresh)) {  // warp-collective TMEM read-modify-write of (this warp's half of) O
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < TC_D / 32; ++c) {
+                for (int c = 0; c < NC; ++c) {
                     uint32_t ov[32];
-                    tmem_ld32(lane_base + 256 + c * 32, ov);
+                    tmem_ld32(lane_base + 256 + (cw * NC + c) * 32, ov);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-                    tmem_st32(lane_base + 256 + c * 32, ov);
+                    tmem_st32(lane_base + 256 + (cw * NC + c) * 32, ov);
                 }
                 tmem_wait_st();
                 l_i *= alpha;
@@ -230,7 +249,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const float mb = m_ref * sl2;
             float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < NC; ++c) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
@@ -241,7 +260,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const uint32_t addr = swz_addr(sP_a, TC_BM, r, c * 4 + g);
+                    const uint32_t addr = swz_addr(sP_a, TC_BM, r, (cw * NC + c) * 4 + g);
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
                                  "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
                 }
@@ -254,11 +273,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(&bar[B_PVDONE], (uint32_t)(n_tiles - 1) & 1u);
         tc_fence_after();
+        if (W8) {  // row sum = the two halves' partial sums
+            float* slot = sHalf + (n_tiles & 1) * 256;
+            slot[cw * 128 + r] = l_i;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            l_i += slot[(cw ^ 1) * 128 + r];
+        }
         const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
-        if (m < L) p.lse[(int64_t)h * p.total + s0 + m] = (l_i > 0.f) ? m_ref * p.scale + logf(l_i) : -INFINITY;
+        if (m < L && cw == 0) p.lse[(int64_t)h * p.total + s0 + m] = (l_i > 0.f) ? m_ref * p.scale + logf(l_i) : -INFINITY;
         __nv_bfloat16* orow = p.o + (int64_t)(s0 + m) * p.o_stride_tok + (int64_t)h * p.o_stride_head;
 #pragma unroll 1
-        for (int c = 0; c < TC_D / 32; ++c) {
+        for (int c = cw * NC; c < cw * NC + NC; ++c) {
             uint32_t ov[32];
             tmem_ld32(lane_base + 256 + c * 32, ov);
             if (m < L) {
@@ -857,6 +882,8 @@ extern "C" int vb200_attn_varlen_fwd_tc(const void* q, const void* k, const void
                                         const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,
                                         int32_t q_heads, int32_t k_heads, int32_t head_dim, const int64_t* st, float scale,
                                         int32_t causal, void* stream) {
+    const bool w8 = (causal >> 8) & 1;  // bit 8: eight softmax warps (experimental, see attn_fwd_tc_kernel)
+    causal &= 1;
     if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_fwd_tc: head_dim must be 128");
     if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_fwd_tc: Hq % Hk != 0");
     for (int i = 0; i < 8; ++i)
@@ -870,16 +897,18 @@ extern "C" int vb200_attn_varlen_fwd_tc(const void* q, const void* k, const void
     AttnTcParams p{};
     p.cu_seqlens = cu_seqlens; p.Hq = q_heads; p.Hk = k_heads; p.total = total; p.scale = scale; p.causal = causal;
     p.o = (__nv_bfloat16*)o; p.o_stride_tok = st[6]; p.o_stride_head = st[7]; p.lse = lse;
-    const size_t smem = (4 + TC_VSTAGES) * TC_TILE + B_COUNT * 8 + 16 + 64;
+    const size_t smem = (4 + TC_VSTAGES) * TC_TILE + B_COUNT * 8 + 16 + 2 * 256 * 4 + 64;  // + the W8 half-row exchange strip
     static bool attr = false;
     if (!attr) {
-        VB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
     p.tiles = (max_seqlen + TC_BM - 1) / TC_BM;
     p.nseq = num_seqs;
     dim3 grid(p.tiles * q_heads * num_seqs);
-    attn_fwd_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    if (w8) attn_fwd_tc_kernel<true><<<grid, 320, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+    else attn_fwd_tc_kernel<false><<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
