@@ -185,6 +185,92 @@ __global__ void k_softmax_tile(uint32_t* out, long long* cyc, int packed) {
     }
 }
 
+// --- the same softmax stage while one thread streams the tile's 20 MMAs (16x M128 N64 K16 + 4x M128 N128 K16) ------
+// Columns 0..255 belong to the softmax warps (as in k_softmax_tile), the MMAs accumulate into 256..511: any slowdown of
+// either side against its solo run is TMEM-port / issue contention, not a data dependence.
+__global__ void __launch_bounds__(288, 1)
+k_softmax_vs_mma(uint32_t* out, long long* cyc_soft, long long* cyc_mma, int run_mma, int run_soft) {
+    extern __shared__ __align__(1024) uint8_t smem[];  // 64 KB of zeros: A [128][128] bf16 + B [128][128] bf16, SWIZZLE_128B boxes
+    __shared__ uint32_t slot;
+    __shared__ uint64_t bar[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 65536 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&slot, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    constexpr int TILES = 128;
+    if (warp == 0) {
+        if (run_mma) {
+            constexpr uint32_t idesc64 = umma_idesc(0, 0, 128, 64), idesc128 = umma_idesc(0, 1, 128, 128);
+            const uint32_t a16 = smem_u32(smem) >> 4, b16 = smem_u32(smem + 32768) >> 4;
+            const long long t0 = clock64();
+            for (int t = 0; t < TILES; ++t) {
+                if (t >= 2) mbar_wait(&bar[t & 1], (uint32_t)((t >> 1) - 1) & 1u);  // at most two tiles of MMAs in flight
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t off = (uint32_t)(k >> 2) * (128 * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16_bo(tmem + 256, a16, off, 16, 1024, b16, off, 16, 1024, idesc64, k ? 1u : 0u);
+                        umma_f16_bo(tmem + 320, a16, off, 16, 1024, b16, off, 16, 1024, idesc64, k ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_bo(tmem + 384, a16, k * 32, 16, 1024, b16, k * 16 * 128, 64 * 128, 1024, idesc128, 1u);
+                    umma_commit(&bar[t & 1]);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&bar[(TILES - 1) & 1], (uint32_t)((TILES - 1) >> 1) & 1u);
+            const long long t1 = clock64();
+            if (lane == 0) cyc_mma[blockIdx.x] = (t1 - t0) / TILES;
+        }
+    } else if (run_soft) {
+        const int sw = warp - 1, q = sw & 3, cw = (sw >> 2) & 1;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = __float_as_uint(0.01f * ((lane + i) & 15));
+        tmem_st32(lane_base + cw * 32, z);
+        tmem_st32(lane_base + 128 + cw * 32, z);
+        tmem_wait_st();
+        const float sl2 = 0.1275f, lse2 = 0.5f, dl = 0.125f;
+        uint32_t acc = 0;
+        const long long t0 = clock64();
+#pragma unroll 1
+        for (int it = 0; it < TILES; ++it) {
+            uint32_t sv[32], dv[32], pk[16];
+            tmem_ld32_nowait(lane_base + cw * 32, sv);
+            tmem_ld32_nowait(lane_base + 128 + cw * 32, dv);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const float p0 = exp2f(__uint_as_float(sv[i]) * sl2 - lse2), p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse2);
+                pk[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(dv[i]) - dl), p1 * (__uint_as_float(dv[i + 1]) - dl));
+            }
+            tmem_st16(lane_base + 64 + cw * 16, pk);
+            tmem_wait_st();
+            acc ^= pk[it & 15];
+        }
+        const long long t1 = clock64();
+        out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+        if (sw == 0 && lane == 0) cyc_soft[blockIdx.x] = (t1 - t0) / TILES;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 static double median_cycles(long long* d_cyc, int blocks) {
     long long* h = (long long*)malloc(sizeof(long long) * blocks);
     cudaMemcpy(h, d_cyc, sizeof(long long) * blocks, cudaMemcpyDeviceToHost);
@@ -235,6 +321,21 @@ int main() {
         cudaDeviceSynchronize();
         const double c = median_cycles(cyc, blocks);
         printf("{\"bench\": \"bwd_softmax_stage_128x64_tile (8 warps, no MMA)\", \"packed_f32x2\": %d, \"clk_per_tile\": %.0f}\n", packed, c);
+    }
+    {
+        long long* cyc2;
+        cudaMalloc(&cyc2, sizeof(long long) * blocks);
+        cudaFuncSetAttribute(k_softmax_vs_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+        const int modes[3][2] = {{1, 0}, {0, 1}, {1, 1}};
+        for (int m = 0; m < 3; ++m) {
+            cudaMemset(cyc, 0, sizeof(long long) * blocks);
+            cudaMemset(cyc2, 0, sizeof(long long) * blocks);
+            for (int rep = 0; rep < 2; ++rep) k_softmax_vs_mma<<<blocks, 288, 65536>>>((uint32_t*)out, cyc, cyc2, modes[m][0], modes[m][1]);
+            cudaDeviceSynchronize();
+            printf("{\"bench\": \"bwd tile: softmax stage vs 20-MMA stream\", \"mma\": %d, \"softmax\": %d, \"softmax_clk_per_tile\": %.0f, "
+                   "\"mma_clk_per_tile\": %.0f}\n", modes[m][0], modes[m][1], median_cycles(cyc, blocks), median_cycles(cyc2, blocks));
+        }
+        cudaFree(cyc2);
     }
     const cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
