@@ -180,7 +180,58 @@ def bench_loss(dev, iters):
     del g32, lr
 
 
-BENCHES = {"rmsnorm": bench_rmsnorm, "rope": bench_rope, "swiglu": bench_swiglu, "loss": bench_loss}
+def bench_fsdp(dev, iters):
+    """FSDP2 copy-in kernels and the gradient-clip kernels at Qwen3-8B layer-unit sizes (193 M parameters per unit)."""
+    import ctypes
+
+    from veomni_b200.clip_grad_norm import multi_scale_, multi_sumsq
+    from veomni_b200.fsdp_comm import pack_plan
+
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    H, I, Hq, Hk, D = 4096, 12288, 32, 8, 128
+    shapes = [(Hq * D, H), (Hk * D, H), (Hk * D, H), (H, Hq * D), (D,), (D,), (I, H), (I, H), (H, I), (H,), (H,)]
+    for world in (2, 8):
+        plan, row = pack_plan(shapes, world)
+        grads = [torch.randn(*s_, device=dev, dtype=BF) for s_ in shapes]
+        out = torch.empty(world * row, device=dev, dtype=BF)
+        flat = []
+        for t, (numel, chunk, off) in zip(grads, plan):
+            flat += [t.data_ptr(), numel, chunk, off]
+        arr = (ctypes.c_int64 * len(flat))(*flat)
+        n = sum(t.numel() for t in grads)
+
+        def pack():
+            lib.vb200_fsdp_pack_bf16(arr, len(plan), world, row, out.data_ptr(), 0, st)
+
+        report(f"fsdp_pack_bf16 (reduce-scatter copy-in)[unit 193M, N={world}]", time_fn(lambda: pack(), [()], iters), nbytes=4 * n)
+
+        def chunk_cat():
+            torch._chunk_cat(grads, dim=0, num_chunks=world, out=out.view(world, -1))
+
+        report(f"(lib) torch._chunk_cat bf16->bf16[unit 193M, N={world}]", time_fn(lambda: chunk_cat(), [()], iters), nbytes=4 * n)
+    # all-gather copy-in: this rank's fp32 shards (1/8 of the unit) cast to bf16
+    shards = [torch.randn((s_[0] + 7) // 8 * (s_[1] if len(s_) > 1 else 1), device=dev) for s_ in shapes]
+    nsh = sum(t.numel() for t in shards)
+    dst = torch.empty(nsh, device=dev, dtype=BF)
+    flat, off = [], 0
+    for t in shards:
+        flat += [t.data_ptr(), t.numel(), t.numel(), off]
+        off += t.numel()
+    arr2 = (ctypes.c_int64 * len(flat))(*flat)
+    report("fsdp_pack_bf16 (all-gather copy-in, fp32->bf16)[unit 193M / 8]",
+           time_fn(lambda: lib.vb200_fsdp_pack_bf16(arr2, len(shards), 1, nsh, dst.data_ptr(), 1, st), [()], iters), nbytes=6 * nsh)
+    big = [torch.randn(64 << 20, device=dev) for _ in range(4)] + [torch.randn(4096, device=dev) for _ in range(64)]
+    tot = sum(t.numel() for t in big)
+    multi_sumsq(big)
+    report("multi_sumsq[256M fp32 + 64 small]", time_fn(lambda: multi_sumsq(big), [()], iters), nbytes=4 * tot)
+    coef = torch.tensor(0.999, device=dev)
+    report("multi_scale[256M fp32 + 64 small]", time_fn(lambda: multi_scale_(big, coef), [()], iters), nbytes=8 * tot)
+    report("(lib) torch._foreach_norm", time_fn(lambda: torch._foreach_norm(big, 2.0), [()], iters), nbytes=4 * tot)
+    report("(lib) torch._foreach_mul_", time_fn(lambda: torch._foreach_mul_(big, coef), [()], iters), nbytes=8 * tot)
+
+
+BENCHES = {"rmsnorm": bench_rmsnorm, "rope": bench_rope, "swiglu": bench_swiglu, "loss": bench_loss, "fsdp": bench_fsdp}
 
 
 def main():
