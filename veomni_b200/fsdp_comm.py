@@ -106,6 +106,7 @@ class B200ReduceScatter(ReduceScatter):
             raise VB200Error(
                 f"B200 reduce-scatter reduces in fp32 (VeOmni's default reduce_dtype, arguments_types.py:248-255); got {input_tensor.dtype}"
             )
+        _RS_INPUTS.pop(input_tensor.data_ptr(), None)  # the copy-in / pre-divide hooks for this buffer have run
         chunk = self._packed.pop(input_tensor.data_ptr(), None)
         if chunk is not None:  # our copy-in left bf16 gradients in the first half of this buffer
             if chunk * world != input_tensor.numel():
