@@ -157,7 +157,12 @@ def run_b200(args) -> None:
     model.init_weights(seed=0)
     model = build_parallelize_model(model, b200_comm=not args.nccl_comm, comm_ctas=args.comm_ctas)
     model.train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
+    if args.b200_adamw:  # experimental multi-tensor AdamW kernel (veomni_b200/optim.py); marks the line
+        from veomni_b200.optim import B200AdamW
+
+        opt = B200AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
 
     # synthetic packed micro-batches in pinned host memory (DummyTextDataset: ids ~ U{0..1023}, first label ignored)
     g = torch.Generator().manual_seed(1234 + rank)
@@ -274,6 +279,7 @@ def run_b200(args) -> None:
                        "global_batch": world, "seq_len": SEQ_LEN, "parallelism": f"fsdp{world}", "layers": cfg.num_hidden_layers,
                        "params_b": round(cfg.num_params() / 1e9, 3), "l2": "inputs (16 GB of bf16 weights per step) larger than L2",
                        "fsdp_comm": "nccl" if args.nccl_comm else "veomni_b200 NVLink pull kernels",
+                       "optimizer": "veomni_b200 multi-tensor AdamW (experimental)" if args.b200_adamw else "torch.optim.AdamW(fused=True)",
                        "valid": args.layers == 0},
             "tokens_per_sec_per_gpu": round(value / world, 1),
             "mfu_measured_peak": round(fpt * value / world / (peaks["bf16_tflops_sustained"] * 1e12), 4),
@@ -313,6 +319,7 @@ def main():
     ap.add_argument("--nccl-comm", action="store_true", help="debug: PyTorch's default NCCL FSDP2 collectives")
     ap.add_argument("--comm-ctas", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--b200-adamw", action="store_true", help="experimental: veomni_b200.optim.B200AdamW instead of torch's fused AdamW")
     ap.add_argument("--skip-no-recompute", action="store_true", help="skip the extra no-recomputation measurement")
     ap.add_argument("--torch-profile", default="", help="debug: write a torch.profiler kernel table of one extra step")
     args = ap.parse_args()

@@ -112,6 +112,16 @@ int vb200_multi_sumsq(const void* const* ptrs_dev, const int64_t* numels_dev, in
 int vb200_multi_scale(void* const* ptrs_dev, const int64_t* numels_dev, int32_t n_entries, int32_t dtype,
                       const float* coef_dev, void* stream);
 
+/* AdamW step on fp32 parameters / gradients / moments over a device table of entries (SURVEY.md §8(f)4 "next":
+ * the reference builds torch.optim.AdamW(fused=True), veomni/optim/optimizer.py:261-328).  Same arithmetic as
+ * PyTorch's fused kernel (ADAMW mode, no amsgrad / maximize); bias_correction1 = 1 - beta1^step,
+ * bias_correction2_sqrt = sqrt(1 - beta2^step), computed by the caller.  grad_scale_dev (optional device scalar)
+ * multiplies every gradient first.  EXPERIMENTAL until validated on hardware.                        */
+int vb200_multi_adamw(void* const* params_dev, const void* const* grads_dev, void* const* exp_avgs_dev,
+                      void* const* exp_avg_sqs_dev, const int64_t* numels_dev, int32_t n_entries, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, float bias_correction1,
+                      float bias_correction2_sqrt, const float* grad_scale_dev, void* stream);
+
 /* ---- softmax cross-entropy over the vocabulary ------------------------------------------
  * Replaces the arithmetic of eager_cross_entropy -> transformers fixed_cross_entropy
  * (veomni/ops/kernels/cross_entropy/eager.py:23-38) and of the liger fused-linear-cross-entropy

@@ -141,6 +141,61 @@ multi_scale_kernel(void* const* __restrict__ ptrs, const int64_t* __restrict__ n
     for (; v0 < nvec; v0 += nthr) stg_stream(xv + v0, scale(ldg_stream(xv + v0)));
 }
 
+
+// AdamW step over a device table of (param, grad, exp_avg, exp_avg_sq, numel) entries, fp32 state and parameters.
+// Arithmetic of torch.optim.AdamW(fused=True) (aten/src/ATen/native/cuda/fused_adam_utils.cuh, ADAMW mode, no
+// amsgrad / maximize):  p -= lr*wd*p;  m = m + (1-b1)*(g - m);  v = b2*v + (1-b2)*g*g;
+//                       p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps).
+// One pass: 16 B read of each of p, g, m, v and 16 B write of p, m, v per 4 elements (28 B/element), which PyTorch's
+// multi_tensor_apply version moves at ~4.5 TB/s on the ~400 Qwen3-8B shards. grad_scale (optional device scalar)
+// multiplies the gradient first, so a clip coefficient can ride along instead of a separate scaling pass.
+struct AdamWArgs {
+    float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2_sqrt;
+};
+
+__global__ void __launch_bounds__(kMtThreads)
+multi_adamw_kernel(void* const* __restrict__ params, const void* const* __restrict__ grads, void* const* __restrict__ exp_avgs,
+                   void* const* __restrict__ exp_avg_sqs, const int64_t* __restrict__ numels, AdamWArgs a,
+                   const float* __restrict__ grad_scale) {
+    float* p = reinterpret_cast<float*>(params[blockIdx.x]);
+    const float* g = reinterpret_cast<const float*>(grads[blockIdx.x]);
+    float* m = reinterpret_cast<float*>(exp_avgs[blockIdx.x]);
+    float* v = reinterpret_cast<float*>(exp_avg_sqs[blockIdx.x]);
+    const int64_t n = numels[blockIdx.x];
+    const float gs = grad_scale ? *grad_scale : 1.0f;
+    const float step_size = a.lr / a.bias_correction1, decay = 1.0f - a.lr * a.weight_decay;
+    const float omb1 = 1.0f - a.beta1, omb2 = 1.0f - a.beta2, inv_bc2s = 1.0f / a.bias_correction2_sqrt;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        gg *= gs;
+        pp *= decay;
+        mm = fmaf(omb1, gg - mm, mm);
+        vv = fmaf(a.beta2, vv, omb2 * gg * gg);
+        pp -= step_size * mm / (sqrtf(vv) * inv_bc2s + a.eps);
+    };
+    const int64_t tid = (int64_t)blockIdx.y * kMtThreads + threadIdx.x;
+    const int64_t nthr = (int64_t)kMtBlocks * kMtThreads;
+    // all four arrays of an entry share their 16-byte phase only if the caller guarantees it (entries are cut at
+    // multiples of 2^20 elements from 256-byte aligned allocations); otherwise the scalar path runs
+    const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+    if (aligned) {
+        const int64_t nvec = n >> 2;
+        for (int64_t i = tid; i < nvec; i += nthr) {
+            float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+            const uint4 gr = ldg_stream(reinterpret_cast<const uint4*>(g) + i);
+            upd(pv.x, __uint_as_float(gr.x), mv.x, vv.x);
+            upd(pv.y, __uint_as_float(gr.y), mv.y, vv.y);
+            upd(pv.z, __uint_as_float(gr.z), mv.z, vv.z);
+            upd(pv.w, __uint_as_float(gr.w), mv.w, vv.w);
+            reinterpret_cast<float4*>(p)[i] = pv;
+            reinterpret_cast<float4*>(m)[i] = mv;
+            reinterpret_cast<float4*>(v)[i] = vv;
+        }
+        for (int64_t i = (nvec << 2) + tid; i < n; i += nthr) upd(p[i], g[i], m[i], v[i]);
+    } else {
+        for (int64_t i = tid; i < n; i += nthr) upd(p[i], g[i], m[i], v[i]);
+    }
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -174,6 +229,24 @@ extern "C" int vb200_multi_scale(void* const* ptrs_dev, const int64_t* numels_de
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == 1) multi_scale_kernel<float><<<grid, kMtThreads, 0, s>>>(ptrs_dev, numels_dev, coef_dev);
     else multi_scale_kernel<__nv_bfloat16><<<grid, kMtThreads, 0, s>>>(ptrs_dev, numels_dev, coef_dev);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_multi_adamw(void* const* params_dev, const void* const* grads_dev, void* const* exp_avgs_dev,
+                                 void* const* exp_avg_sqs_dev, const int64_t* numels_dev, int32_t n_entries, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, float bias_correction1,
+                                 float bias_correction2_sqrt, const float* grad_scale_dev, void* stream) {
+    if (n_entries == 0) return VB200_OK;
+    if (n_entries < 0 || !params_dev || !grads_dev || !exp_avgs_dev || !exp_avg_sqs_dev || !numels_dev)
+        return vb200_set_error(VB200_EINVAL, "multi_adamw: bad arguments");
+    if (!(bias_correction1 > 0.f) || !(bias_correction2_sqrt > 0.f))
+        return vb200_set_error(VB200_EINVAL, "multi_adamw: bias corrections must be positive (step >= 1)");
+    AdamWArgs a{lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2_sqrt};
+    dim3 grid(n_entries, kMtBlocks);
+    multi_adamw_kernel<<<grid, kMtThreads, 0, (cudaStream_t)stream>>>(params_dev, grads_dev, exp_avgs_dev, exp_avg_sqs_dev, numels_dev, a,
+                                                                       grad_scale_dev);
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
