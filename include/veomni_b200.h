@@ -50,6 +50,14 @@ int vb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_
 /* dx: [rows, cols] bf16; dw_partial: [vb200_rmsnorm_bwd_partials(rows, cols), cols] fp32
  * workspace; dw: [cols] fp32 = column sums (deterministic two-pass reduction).            */
 int64_t vb200_rmsnorm_bwd_partials(int64_t rows, int64_t cols);
+/* Fused residual add + RMSNorm (the `hidden_states = residual + hidden_states` line before every
+ * Qwen3RMSNorm in the decoder layer, patched_modeling_qwen3_gpu.py:369-375). EXPERIMENTAL until validated on hardware.
+ *   fwd: h_out = bf16(x + residual), y = RMSNorm(h_out) * w, rstd[rows];  cols in {1024, 2048, 4096, 5120, 8192}
+ *   bwd: dx = rmsnorm_bwd(dy; x = h_out, w, rstd) + dres (bf16 sum), dw as vb200_rmsnorm_bwd; dres NULL = plain bwd */
+int vb200_add_rmsnorm_fwd(const void* x, const void* residual, const void* w, void* h_out, void* y, float* rstd,
+                          int64_t rows, int64_t cols, float eps, void* stream);
+int vb200_rmsnorm_bwd_add(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                          float* dw_partial, float* dw, int64_t rows, int64_t cols, void* stream);
 int vb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, void* dx,
                       float* dw_partial, float* dw, int64_t rows, int64_t cols, void* stream);
 

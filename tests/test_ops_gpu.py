@@ -248,3 +248,27 @@ def test_b200_adamw_matches_torch_fused(cuda_dev):
     o_mine.step(grad_scale=torch.tensor(0.25, device=cuda_dev))
     for a, b in zip(ref, mine):
         torch.testing.assert_close(b, a, atol=1e-7, rtol=2e-6)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("VB200_EXPERIMENTAL", "0") != "1", reason="experimental: set VB200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("rows,cols", [(1, 1024), (37, 2048), (4096, 4096), (65, 5120), (9, 8192)])
+def test_fused_add_rms_norm_equals_add_then_norm(cuda_dev, rows, cols):
+    """fused_add_rms_norm == (residual + x in bf16, then rms_norm): forward bit-exact (same rounding points), backward
+    equal to autograd through the unfused pair up to the bf16 rounding of the gradient sum (1 ulp)."""
+    from veomni_b200 import functional as F
+
+    g = torch.Generator().manual_seed(rows + cols)
+    x, r = (torch.randn(rows, cols, generator=g).to(BF).to(cuda_dev) for _ in range(2))
+    w = (1 + 0.1 * torch.randn(cols, generator=g)).to(BF).to(cuda_dev)
+    dy, dh = (torch.randn(rows, cols, generator=g).to(BF).to(cuda_dev) for _ in range(2))
+    xa, ra, wa = (t.clone().requires_grad_(True) for t in (x, r, w))
+    y1, h1 = F.fused_add_rms_norm(xa, ra, wa, 1e-6)
+    (y1.float() * dy.float()).sum().add((h1.float() * dh.float()).sum()).backward()
+    xb, rb, wb = (t.clone().requires_grad_(True) for t in (x, r, w))
+    h2 = rb + xb
+    y2 = F.rms_norm(h2, wb, 1e-6)
+    (y2.float() * dy.float()).sum().add((h2.float() * dh.float()).sum()).backward()
+    assert torch.equal(h1, h2) and torch.equal(y1, y2)
+    _close(xa.grad, xb.grad, atol=2e-2, rtol=8e-3, what="dx")
+    _close(ra.grad, rb.grad, atol=2e-2, rtol=8e-3, what="dresidual")
+    _close(wa.grad, wb.grad, atol=1e-1, rtol=2e-2, what="dw")

@@ -47,6 +47,8 @@ SIGNATURES = {
     "vb200_multi_sumsq_partials": (c_int64, [_I32]),
     "vb200_multi_sumsq": (c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P]),
     "vb200_multi_scale": (c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "vb200_add_rmsnorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _P]),
+    "vb200_rmsnorm_bwd_add": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "vb200_multi_adamw": (c_int, [_P, _P, _P, _P, _P, _I32, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
     "vb200_cross_entropy": (c_int, [_P, _I32, _I64, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _I64, _F, _P, _P, _P]),
     "vb200_count_valid_labels": (c_int, [_P, _I64, _I64, _P, _P]),

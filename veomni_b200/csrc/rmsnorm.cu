@@ -241,6 +241,126 @@ rmsnorm_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
     }
 }
 
+// ---- fused residual-add + RMSNorm (EXPERIMENTAL until validated on hardware) -------------------
+// Forward: h = bf16(x + residual) (the new residual stream, as the reference's `hidden_states = residual +
+// hidden_states` rounds it), y = bf16(w * bf16(h * rstd)) — one pass over x and residual instead of an elementwise add
+// kernel followed by the norm. One warp per row, the row's h kept packed in registers between the two sweeps;
+// H = NCH * 256 elements.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+add_rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                       const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ y,
+                       float* __restrict__ rstd, int64_t rows, float eps) {
+    constexpr int H = NCH * 256;
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
+    for (int64_t row = wid; row < rows; row += nw) {
+        const __nv_bfloat16 *xr = x + row * H, *rr = res + row * H;
+        uint4 hv[NCH];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            float a[8], b[8];
+            unpack8(ldg_stream(xr + (k * 32 + lane) * 8), a);
+            unpack8(ldg_stream(rr + (k * 32 + lane) * 8), b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = round_bf16(a[i] + b[i]);
+                ss = fmaf(a[i], a[i], ss);
+            }
+            hv[k] = pack8(a);
+            stg_stream(h_out + row * H + (k * 32 + lane) * 8, hv[k]);
+        }
+        ss = warp_sum(ss);
+        const float rs = rsqrtf(ss * (1.0f / (float)H) + eps);
+        if (lane == 0) rstd[row] = rs;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            float a[8], wf[8];
+            unpack8(hv[k], a);
+            unpack8(*reinterpret_cast<const uint4*>(w + (k * 32 + lane) * 8), wf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = wf[i] * round_bf16(a[i] * rs);
+            stg_stream(y + row * H + (k * 32 + lane) * 8, pack8(a));
+        }
+    }
+}
+
+// Backward of the fused op: dx = dresidual = rmsnorm_bwd(dy; h, w, rstd) + dh, where dh is the gradient that reaches
+// h through the residual stream (summed and rounded to bf16 as autograd's accumulation of two bf16 gradients does).
+// Same structure as rmsnorm_bwd_wide_kernel, plus the dh stream.
+template <int THREADS, int V>
+__global__ void __launch_bounds__(THREADS)
+rmsnorm_bwd_wide_add_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                            const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
+                            const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+                            float* __restrict__ dw_partial, int64_t rows, int cols) {
+    constexpr int NW = THREADS / 32;
+    __shared__ float red[2][NW];
+    const int nvec = cols >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float wf[V][8], dwacc[V][8];
+    bool act[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int v = threadIdx.x + k * THREADS;
+        act[k] = v < nvec;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { wf[k][i] = 0.f; dwacc[k][i] = 0.f; }
+        if (act[k]) unpack8(reinterpret_cast<const uint4*>(w)[v], wf[k]);
+    }
+    const float inv_cols = 1.0f / (float)cols;
+    int it = 0;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x, ++it) {
+        const float rs = rstd[r];
+        float g[V][8], xh[V][8];
+        uint4 dr[V];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (act[k]) {
+                const int64_t off = r * cols + (int64_t)(threadIdx.x + k * THREADS) * 8;
+                float d[8], xx[8];
+                unpack8(ldg_stream(dy + off), d);
+                unpack8(ldg_stream(x + off), xx);
+                dr[k] = ldg_stream(dres + off);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    xh[k][i] = xx[i] * rs;
+                    g[k][i] = d[i] * wf[k][i];
+                    dot = fmaf(g[k][i], xh[k][i], dot);
+                    dwacc[k][i] = fmaf(d[i], round_bf16(xh[k][i]), dwacc[k][i]);
+                }
+            }
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) red[it & 1][warp] = dot;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) tot += red[it & 1][i];
+        const float c = tot * inv_cols;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (act[k]) {
+                float o[8], e[8];
+                unpack8(dr[k], e);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = round_bf16(rs * (g[k][i] - xh[k][i] * c)) + e[i];  // bf16 + bf16 -> bf16
+                stg_stream(dx + r * cols + (int64_t)(threadIdx.x + k * THREADS) * 8, pack8(o));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        if (act[k]) {
+            float* dst = dw_partial + (int64_t)blockIdx.x * cols + (int64_t)(threadIdx.x + k * THREADS) * 8;
+            *reinterpret_cast<float4*>(dst) = make_float4(dwacc[k][0], dwacc[k][1], dwacc[k][2], dwacc[k][3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(dwacc[k][4], dwacc[k][5], dwacc[k][6], dwacc[k][7]);
+        }
+    }
+}
+
 // Narrow rows: TPR lanes per row, CTA of 256 threads handles 256/TPR rows per iteration.
 template <int TPR>
 __global__ void __launch_bounds__(256)
@@ -415,6 +535,60 @@ extern "C" int vb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, c
     else if (nvec <= 1024) WIDE(512, 2);
     else WIDE(512, 4);
 #undef SMALL
+#undef WIDE
+    VB_HOST_CHECK_LAUNCH();
+    colsum_kernel<<<(int)((cols + 31) / 32), 256, 0, st>>>(dw_partial, dw, g, (int)cols);
+    vb200_count_launch(2);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_add_rmsnorm_fwd(const void* x, const void* residual, const void* w, void* h_out, void* y, float* rstd,
+                                     int64_t rows, int64_t cols, float eps, void* stream) {
+    if (rows < 0 || !x || !residual || !w || !h_out || !y || !rstd) return vb200_set_error(VB200_EINVAL, "add_rmsnorm_fwd: bad arguments");
+    if (rows == 0) return VB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+#define GO(N)                                                                                                               \
+    add_rmsnorm_fwd_kernel<N><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,     \
+                                                                (const __nv_bfloat16*)w, (__nv_bfloat16*)h_out,              \
+                                                                (__nv_bfloat16*)y, rstd, rows, eps)
+    switch (cols) {
+        case 1024: GO(4); break;
+        case 2048: GO(8); break;
+        case 4096: GO(16); break;
+        case 5120: GO(20); break;
+        case 8192: GO(32); break;
+        default: return vb200_set_error(VB200_EINVAL, "add_rmsnorm_fwd: hidden size must be 1024, 2048, 4096, 5120 or 8192");
+    }
+#undef GO
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_rmsnorm_bwd_add(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                                     float* dw_partial, float* dw, int64_t rows, int64_t cols, void* stream) {
+    if (!dres) return vb200_rmsnorm_bwd(dy, x, w, rstd, dx, dw_partial, dw, rows, cols, stream);
+    if (rows < 0 || cols < 264 || (cols & 7) || cols > 16384)
+        return vb200_set_error(VB200_EINVAL, "rmsnorm_bwd_add: cols must be a multiple of 8 in [264,16384]");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) {
+        VB_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * cols, st));
+        return VB200_OK;
+    }
+    const int nvec = (int)(cols >> 3);
+    const int g = bwd_grid(rows, (int)cols);
+#define WIDE(T, V)                                                                                                         \
+    rmsnorm_bwd_wide_add_kernel<T, V><<<g, T, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,                   \
+                                                       (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,           \
+                                                       (__nv_bfloat16*)dx, dw_partial, rows, (int)cols)
+    if (nvec <= 128) WIDE(128, 1);
+    else if (nvec <= 256) WIDE(256, 1);
+    else if (nvec <= 512) WIDE(512, 1);
+    else if (nvec <= 1024) WIDE(512, 2);
+    else WIDE(512, 4);
 #undef WIDE
     VB_HOST_CHECK_LAUNCH();
     colsum_kernel<<<(int)((cols + 31) / 32), 256, 0, st>>>(dw_partial, dw, g, (int)cols);

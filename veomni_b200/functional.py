@@ -85,6 +85,54 @@ def rms_norm(hidden_states: torch.Tensor, weight: torch.Tensor, eps: float) -> t
     return _RMSNorm.apply(hidden_states, weight, eps)
 
 
+class _AddRMSNorm(torch.autograd.Function):
+    """(y, h) = (RMSNorm(x + residual) * w, x + residual) in one pass; EXPERIMENTAL (not yet validated on hardware)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float):
+        _need_cuda_bf16(x)
+        _need_cuda_bf16(residual)
+        if x.shape != residual.shape:
+            raise VB200Error("fused_add_rms_norm: x and residual must have the same shape")
+        cols = x.shape[-1]
+        x2 = _aligned(x.reshape(-1, cols).contiguous())
+        r2 = _aligned(residual.reshape(-1, cols).contiguous())
+        w = _aligned(weight.detach().to(torch.bfloat16).contiguous())
+        rows = x2.shape[0]
+        h, y = torch.empty_like(x2), torch.empty_like(x2)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_lib.load().vb200_add_rmsnorm_fwd(x2.data_ptr(), r2.data_ptr(), w.data_ptr(), h.data_ptr(), y.data_ptr(),
+                                                    rstd.data_ptr(), rows, cols, float(eps), stream_ptr()), "vb200_add_rmsnorm_fwd")
+        ctx.save_for_backward(h, w, rstd)
+        ctx.x_shape, ctx.w_dtype = x.shape, weight.dtype
+        return y.view(x.shape), h.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor, dh: torch.Tensor | None):
+        h, w, rstd = ctx.saved_tensors
+        rows, cols = h.shape
+        dy2 = _aligned(dy.reshape(rows, cols).contiguous())
+        dh2 = _aligned(dh.reshape(rows, cols).contiguous()) if dh is not None else None
+        lib = _lib.load()
+        dx = torch.empty_like(h)
+        partial = torch.empty(max(lib.vb200_rmsnorm_bwd_partials(rows, cols), 1), cols, dtype=torch.float32, device=h.device)
+        dw = torch.empty(cols, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            check(lib.vb200_rmsnorm_bwd_add(dy2.data_ptr(), h.data_ptr(), w.data_ptr(), rstd.data_ptr(),
+                                            dh2.data_ptr() if dh2 is not None else None, dx.data_ptr(), partial.data_ptr(),
+                                            dw.data_ptr(), rows, cols, stream_ptr()), "vb200_rmsnorm_bwd_add")
+        dx = dx.view(ctx.x_shape)
+        return dx, dx, dw.to(ctx.w_dtype), None
+
+
+def fused_add_rms_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float):
+    """``h = residual + x`` (bf16) and ``rms_norm(h, weight, eps)`` in one kernel; returns ``(normed, h)``.
+    Replaces the `hidden_states = residual + hidden_states` + RMSNorm pair of the decoder layer
+    (patched_modeling_qwen3_gpu.py:369-375). Experimental: off by default in the callers."""
+    return _AddRMSNorm.apply(x, residual, weight, eps)
+
+
 # ----------------------------------------------------------------------------------------------
 # RoPE
 # ----------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ plugs the same kernels into its OpSlots instead.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -148,9 +149,15 @@ class Qwen3DecoderLayer(nn.Module):
         self.mlp = Qwen3MLP(cfg)
         self.input_layernorm = Qwen3RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
         self.post_attention_layernorm = Qwen3RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+        self.fuse_add_norm = os.environ.get("VB200_FUSE_ADD_NORM", "0") == "1"
 
     def forward(self, h, cos, sin, cu_seqlens, max_seqlen, sp_group=None):
-        h = h + self.self_attn(self.input_layernorm(h), cos, sin, cu_seqlens, max_seqlen, sp_group)
+        a = self.self_attn(self.input_layernorm(h), cos, sin, cu_seqlens, max_seqlen, sp_group)
+        if self.fuse_add_norm:  # experimental: residual add fused into the post-attention RMSNorm
+            n = self.post_attention_layernorm
+            x, h = F.fused_add_rms_norm(a, h, n.weight, n.variance_epsilon)
+            return h + self.mlp(x)
+        h = h + a
         return h + self.mlp(self.post_attention_layernorm(h))
 
 
