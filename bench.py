@@ -240,6 +240,8 @@ def run_b200(args) -> None:
                      "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1)}
         except torch.OutOfMemoryError:
             no_rc = {"value": None, "note": "out of memory without recomputation"}
+        except Exception as ex:  # noqa: BLE001  (a side measurement must never take the headline line down with it)
+            no_rc = {"value": None, "note": f"{type(ex).__name__}: {str(ex)[:160]}"}
         inner.gradient_checkpointing = prev
     if args.torch_profile:  # debugging aid, outside every timed region: per-kernel device time of one step on rank 0
         from torch.profiler import ProfilerActivity, profile
