@@ -3,14 +3,24 @@
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        bench.py --gpus N --steps K --warmup W
+        bench.py --gpus N --steps K --warmup W [--workload qwen3_8b|ulysses32k|moe30b]
     python bench.py --impl reference ...      # the reference's eager CPU path on this box's host cores
 
-One "step" = forward + backward (per-layer gradient checkpointing, as VeOmni's default) + grad-norm clip +
-fused AdamW step + zero_grad of the full Qwen3-8B (36 layers, 8.19 B params, random init) under FSDP2
-(bf16 params / fp32 reduce), one packed 4096-token micro-batch per rank (weak scaling).  Every op on the
-hot path (RMSNorm, q/k-norm+RoPE, varlen attention, SwiGLU, FSDP2 all-gather / reduce-scatter) is a
-veomni_b200 sm_100a kernel; dense projections are cuBLAS.  Prints ONE JSON line (rank 0).
+One "step" = forward + backward (per-layer gradient checkpointing, as VeOmni's default) + grad-norm clip + AdamW step +
+zero_grad of the full model (random init), one packed micro-batch per data-parallel rank (weak scaling). Every op on the
+hot path (RMSNorm, q/k-norm+RoPE, varlen attention, SwiGLU / MoE route + GroupGEMM, fused linear-cross-entropy, FSDP2
+all-gather / reduce-scatter, Ulysses all-to-all, EP dispatch / combine, clip and AdamW) is a veomni_b200 sm_100a kernel;
+dense projections are cuBLAS. Prints ONE JSON line (rank 0).
+
+Workloads (BASELINE.json configs):
+  qwen3_8b    configs[1]  Qwen3-8B FSDP2 bf16 seq 4096, DP only — the headline. At 1 GPU the model is NOT wrapped in FSDP
+                          (as the reference: veomni/distributed/torch_parallelize.py:438-440,465).
+  ulysses32k  configs[2]  Qwen3-8B FSDP2 + Ulysses SP degree 4 (degree = world if world < 4), one 32768-token sample per SP group
+  moe30b      configs[3]  Qwen3-30B-A3B FSDP2 + EP degree = world (8 in the config), GroupGEMM path, seq 4096
+
+At world > 1 the line carries "parity" (bit-exact checks of the NVLink collectives against NCCL-moved expected data and
+FSDP2 gradients vs PyTorch's NCCL comm, run in this very process group before the timed region), "comm" (achieved NVLink
+GB/s of the FSDP kernels inside the step) and "nccl_ab" (the same step on PyTorch's default NCCL FSDP2 collectives).
 """
 from __future__ import annotations
 
@@ -28,7 +38,7 @@ sys.path.insert(0, str(REPO))
 
 SEQ_LEN = 4096
 METRIC = "tokens/sec (Qwen3-8B FSDP2 bf16 seq4096)"
-
+CPU_SAMPLE_TOKENS = 256  # the bounded CPU sample: one definition for `cpu_baseline` and `--impl reference`
 
 # DRAM bytes per launch (read + write) of the three attention kernels at T=4096, 32/8 heads, D=128, from ncu --set full
 NCU_TRAFFIC_BYTES = {"bwd_dkdv": 86041088 + 4705024, "bwd_dq": 84966656 + 11869440, "fwd": 50374400 + 3454208}
@@ -78,30 +88,56 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(sample_tokens: int, iters: int, threads: int | None) -> dict:
-    """The reference's eager CPU path (restated in oracle/qwen3_cpu.py) on a bounded sample."""
+# CPU arm: the reference's eager path (restated in oracle/qwen3_cpu.py) on a bounded sample of the workload
+# ------------------------------------------------------------------------------------------------
+def _pick_threads() -> int:
     import torch
 
-    from oracle.qwen3_cpu import time_layer_step
-
     ncpu = os.cpu_count() or 1
-    if threads:
-        cores = threads
-    else:
-        # all host threads are available to the reference arm, but small bf16 GEMMs stop scaling (and slow down) long
-        # before 128 threads: pick the fastest thread count on a 64-token probe and report the count actually used
-        cand = sorted({c for c in (ncpu, ncpu // 2, ncpu // 4, 32, 16) if 1 <= c <= ncpu})
-        probe = {c: time_layer_step(tokens=64, iters=1, threads=c) for c in cand}
-        cores = min(probe, key=probe.get)
+    # all host threads are available to the CPU arm, but bf16 GEMMs of this size stop scaling long before 128+ threads:
+    # time a small matmul at a few thread counts and keep the fastest
+    best, best_t = ncpu, float("inf")
+    a, b = torch.randn(256, 4096).bfloat16(), torch.randn(12288, 4096).bfloat16()
+    for c in sorted({c for c in (ncpu, ncpu // 2, ncpu // 4, 32, 16) if 1 <= c <= ncpu}):
+        torch.set_num_threads(c)
+        torch.nn.functional.linear(a, b)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.linear(a, b)
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best, best_t = c, t
+    return best
+
+
+def cpu_sample(steps: int, warmup: int, budget_s: float) -> dict:
+    """Time `steps` sample steps (after `warmup`) of oracle.qwen3_cpu.SampleStep; stops early past `budget_s` seconds."""
+    import torch
+
+    from oracle.qwen3_cpu import SampleStep
+
+    cores = _pick_threads()
     torch.set_num_threads(cores)
-    t_layer = time_layer_step(tokens=sample_tokens, iters=iters, threads=cores)
-    # 36 identical layers; per-token cost measured at `sample_tokens` (attention's quadratic term is
-    # under-counted at 4096; embedding, lm_head, loss and optimizer are not counted: an optimistic CPU number)
-    step_s = t_layer * 36 * (SEQ_LEN / sample_tokens)
-    return {"value": round(SEQ_LEN / step_s, 3), "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": f"1 of 36 Qwen3-8B decoder layers, fwd + recompute + bwd in bf16 on {sample_tokens} tokens, "
-                      f"best of {iters}; scaled x36 layers x{SEQ_LEN // sample_tokens} to a 4096-token step",
-            "seconds_per_sample": round(t_layer, 3)}
+    t_init = time.perf_counter()
+    s = SampleStep(tokens=CPU_SAMPLE_TOKENS, layers=36, threads=cores, seq_len=SEQ_LEN)
+    t_init = time.perf_counter() - t_init
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        s.run()
+        if time.perf_counter() - t_start > budget_s / 3:
+            break
+    times = []
+    for _ in range(max(1, steps)):
+        times.append(s.run())
+        if time.perf_counter() - t_start > budget_s:
+            break
+    sec = sum(times) / len(times)
+    return {"value": round(CPU_SAMPLE_TOKENS / sec, 3), "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"one sample step = the full Qwen3-8B (36 layers + embedding + lm_head + causal-LM loss, bf16 eager ops as in "
+                      f"oracle/qwen3_cpu.py) forward + per-layer recompute + backward on {CPU_SAMPLE_TOKENS} of the step's {SEQ_LEN} "
+                      f"tokens, clip_grad_norm, and AdamW over {CPU_SAMPLE_TOKENS}/{SEQ_LEN} of the 8.19 B fp32 parameters; every step "
+                      f"really executed (no extrapolation); {len(times)} timed steps, mean",
+            "seconds_per_sample_step": round(sec, 3), "steps_timed": len(times), "init_s": round(t_init, 1), "loss": round(s.loss, 4)}
 
 
 def run_reference(args) -> None:
@@ -109,12 +145,13 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     t0 = time.time()
-    base = cpu_baseline(sample_tokens=512, iters=max(1, min(args.steps, 3)), threads=None)
+    base = cpu_sample(steps=args.steps, warmup=min(args.warmup, 1), budget_s=150.0)
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "tokens/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(SEQ_LEN / base["value"] * 1e3, 1),
+           "steps": base["steps_timed"], "warmup": min(args.warmup, 1), "ms_per_step": round(base["seconds_per_sample_step"] * 1e3, 1),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-           "config": {"workload": "Qwen3-8B FSDP2 bf16 seq_len 4096 training step (BASELINE configs[1]), reference eager ops on host CPU",
-                      "global_batch": 1, "seq_len": SEQ_LEN},
+           "config": {"workload": f"Qwen3-8B bf16 seq_len 4096 training step (BASELINE configs[1]) on host CPU cores, reference eager ops; "
+                                  f"each timed step is a bounded {CPU_SAMPLE_TOKENS}-token sample of the {SEQ_LEN}-token step (see cpu_baseline.sample)",
+                      "global_batch": 1, "seq_len": SEQ_LEN, "sample_tokens": CPU_SAMPLE_TOKENS},
            "cpu_baseline": base,
            "e2e": {"value": base["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(time.time() - t0, 1)}
@@ -140,50 +177,105 @@ def run_b200(args) -> None:
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
 
-    from veomni_b200 import _lib
+    from veomni_b200 import _lib, prof
     from veomni_b200 import attention as vattn
     from veomni_b200.clip_grad_norm import clip_grad_norm
     from veomni_b200.host_qwen3 import Qwen3Config, Qwen3ForCausalLM, flops_per_token
+    from veomni_b200.optim import B200AdamW
+    from veomni_b200.parallel_state import init_parallel_state
     from veomni_b200.parallelize import build_parallelize_model
 
     _lib.load()  # fail loudly if the CUDA library is missing
-    cfg = Qwen3Config.qwen3_8b()
+    wl = args.workload
+    sp = 1
+    seq_len = SEQ_LEN
+    if wl == "ulysses32k":
+        sp = 4 if world % 4 == 0 else world
+        seq_len = 32768
+        if world < 2:
+            raise SystemExit("--workload ulysses32k needs at least 2 GPUs")
+    dp = world // sp
+    ep = world if wl == "moe30b" else 1
+    if wl == "moe30b" and world < 2:
+        raise SystemExit("--workload moe30b needs at least 2 GPUs (expert parallelism)")
+    if world > 1:
+        init_parallel_state(dp_size=dp, dp_shard_size=dp, ulysses_size=sp, ep_size=ep)
+    if wl == "moe30b":
+        from veomni_b200.host_qwen3_moe import Qwen3MoeConfig, Qwen3MoeForCausalLM
+
+        cfg = Qwen3MoeConfig.qwen3_30b_a3b()
+    else:
+        cfg = Qwen3Config.qwen3_8b()
     if args.layers:
         cfg.num_hidden_layers = args.layers  # debugging only; reported in config and marks the run invalid
     with torch.device("meta"):
-        model = Qwen3ForCausalLM(cfg)
-    model.to_empty(device=dev)
-    model.inv_freq.copy_(1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, device=dev).float() / cfg.head_dim)))
-    model.init_weights(seed=0)
-    model = build_parallelize_model(model, b200_comm=not args.nccl_comm, comm_ctas=args.comm_ctas)
-    model.train()
-    if args.b200_adamw:  # experimental multi-tensor AdamW kernel (veomni_b200/optim.py); marks the line
-        from veomni_b200.optim import B200AdamW
-
-        opt = B200AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0)
+        model = Qwen3MoeForCausalLM(cfg) if wl == "moe30b" else Qwen3ForCausalLM(cfg)
+    reshard = bool(args.reshard)
+    comm_kw = dict(b200_comm=not args.nccl_comm, comm_ctas=args.comm_ctas, rs_mode=args.rs_mode, fuse_copy_out=not args.no_fuse_copy_out,
+                   enable_reshard_after_forward=reshard)
+    if wl == "moe30b":
+        # 30.5 B parameters never exist unsharded: slice / shard on the meta device, then materialise and initialise the shards
+        model = build_parallelize_model(model, init_device="meta", **comm_kw)
     else:
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
+        model.to_empty(device=dev)
+        model.init_weights(seed=0)
+        model = build_parallelize_model(model, **comm_kw)
+    inner = model
+    inner.inv_freq = (1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, device=dev).float() / cfg.head_dim)))
+    model.train()
+    if sp > 1:
+        from veomni_b200.parallel_state import get_parallel_state
 
-    # synthetic packed micro-batches in pinned host memory (DummyTextDataset: ids ~ U{0..1023}, first label ignored)
-    g = torch.Generator().manual_seed(1234 + rank)
+        model.sp_group = get_parallel_state().ulysses_group
+    if ep > 1:
+        from veomni_b200 import moe as vmoe
+        from veomni_b200.ep import EPContext
+        from veomni_b200.parallel_state import get_parallel_state
+
+        vmoe.set_ep_group(EPContext(get_parallel_state().ep_group))
+    fsdp = world > 1
+    if args.torch_adamw:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
+    else:
+        # one multi-tensor kernel; at 1 GPU it owns the fp32 masters and the model computes on the bf16 copy it maintains
+        opt = B200AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, master_weights=not fsdp)
+    if not fsdp and args.torch_adamw:
+        model.to(torch.bfloat16)  # debugging: pure-bf16 parameters with torch's optimizer
+    fold_clip = (not args.torch_adamw) and ep == 1
+
+    # synthetic packed micro-batches in pinned host memory (DummyTextDataset: ids ~ U{0..1023}, first label ignored);
+    # under Ulysses every rank of an SP group holds its contiguous slice of the same sample (SequenceParallelCollator)
+    t_local = seq_len // sp
+    sp_rank, dp_rank = rank % sp, rank // sp
+    g = torch.Generator().manual_seed(1234 + dp_rank)
     nbuf = 4
     host = []
     for _ in range(nbuf):
-        ids = torch.randint(0, 1024, (1, SEQ_LEN), generator=g, dtype=torch.int64)
+        ids = torch.randint(0, 1024, (1, seq_len), generator=g, dtype=torch.int64)
         labels = ids.clone()
         labels[0, 0] = -100
-        pos = torch.arange(SEQ_LEN, dtype=torch.int64)[None]
-        host.append(tuple(t.pin_memory() for t in (ids, labels, pos)))
-    cu = torch.tensor([0, SEQ_LEN], dtype=torch.int32, device=dev)
+        shift = torch.nn.functional.pad(labels, (0, 1), value=-100)[..., 1:]
+        pos = torch.arange(seq_len, dtype=torch.int64)[None]
+        sl = slice(sp_rank * t_local, (sp_rank + 1) * t_local)
+        host.append(tuple(t[:, sl].contiguous().pin_memory() for t in (ids, shift, pos)))
+    cu = torch.tensor([0, seq_len], dtype=torch.int32, device=dev)
     resident = [tuple(t.to(dev) for t in h) for h in host]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    n_valid_local = [int((h[1] != -100).sum()) for h in host]
+    sp_group = getattr(model, "sp_group", None)
 
-    def step(batch):
-        ids, labels, pos = batch
-        loss = model(ids, pos, cu, SEQ_LEN, labels=labels)
+    def step(batch, i=0):
+        ids, shift, pos = batch
+        loss = model(ids, pos, cu, seq_len, shift_labels=shift)
+        if sp > 1:  # mean over the SP group's valid tokens (sequence_parallel/loss.py): local mean * n_local / n_group
+            loss = loss * (n_valid_local[i % nbuf] * sp / float(seq_len - 1))
         loss.backward()
-        clip_grad_norm(model, 1.0)  # veomni_clip_grad_norm semantics, multi-tensor kernels
-        opt.step()
+        if fold_clip:
+            _, coef = clip_grad_norm(model, 1.0, return_coef=True)  # veomni_clip_grad_norm semantics; the scaling pass
+            opt.step(grad_scale=coef)                               # is folded into the AdamW kernel
+        else:
+            clip_grad_norm(model, 1.0)
+            opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
 
@@ -196,9 +288,9 @@ def run_b200(args) -> None:
         for i in range(nsteps):
             if e2e:
                 batch = tuple(t.to(dev, non_blocking=True) for t in host[i % nbuf])
-                last = step(batch).item()  # device->host read of the step's loss
+                last = step(batch, i).item()  # device->host read of the step's loss
             else:
-                last = step(resident[i % nbuf])
+                last = step(resident[i % nbuf], i)
         e.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -206,44 +298,80 @@ def run_b200(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item() / nsteps, (last if isinstance(last, float) else float(last.item()))
 
+    # ---- multi-GPU parity, in this process group, before anything is timed ------------------------------------------
+    parity = None
+    if fsdp and not args.skip_parity and not args.nccl_comm:
+        from veomni_b200 import selfcheck
+
+        t0 = time.time()
+        symm = getattr(model, "_vb200_symm", None)
+        if symm is not None and symm.world == world:
+            parity = selfcheck.run_all(symm, dev, fsdp=True, ep=True)  # raises VB200Error on any mismatch
+        elif symm is not None:
+            parity = selfcheck.run_all(symm, dev, fsdp=False, ep=False)
+            parity["note"] = f"collectives checked on the {symm.world}-rank FSDP shard group"
+        if parity is not None:
+            parity["seconds"] = round(time.time() - t0, 1)
+        torch.cuda.synchronize()
+        dist.barrier()
+
     for i in range(args.warmup):
-        step(resident[i % nbuf])
+        step(resident[i % nbuf], i)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     _lib.reset_launch_count()
-    # CUDA-event pairs around every launch of the three attention kernels (the heaviest kernels of ours)
+    # CUDA-event pairs around every launch of the attention kernels (the heaviest kernels of ours) and the collectives
     vattn.PROFILE = {"fwd": [], "bwd_dq": [], "bwd_dkdv": []}
+    prof.ACTIVE = {"fsdp_all_gather": [], "fsdp_reduce_scatter": [], "ulysses_a2a": [], "ep_pull": [], "group_gemm": []}
     ms_dev, loss_dev = timed(args.steps, e2e=False)
     launches = _lib.launch_count()
-    prof = vattn.PROFILE
-    vattn.PROFILE = None
+    aprof, vattn.PROFILE = vattn.PROFILE, None
+    cprof, prof.ACTIVE = prof.ACTIVE, None
     torch.cuda.synchronize()
-    prof_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in prof.items()}
+    prof_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in aprof.items()}
+    comm_stats = prof.summarize(cprof)
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
     mem_gb = torch.cuda.max_memory_allocated() / 2**30
-    # The same step with every activation kept instead of recomputed (180 GB of HBM3e hold them at this size): reported
-    # next to the headline, which keeps the reference's default of per-layer gradient checkpointing.
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- side measurements (outside the timed regions; none of them can take the headline line down) ---------------
     no_rc = None
-    if not args.skip_no_recompute:
-        inner = getattr(model, "module", model)
+    if not args.skip_no_recompute and wl == "qwen3_8b":
         prev = inner.gradient_checkpointing
         inner.gradient_checkpointing = False
         try:
             torch.cuda.reset_peak_memory_stats()
             for i in range(2):
-                step(resident[i % nbuf])
+                step(resident[i % nbuf], i)
             ms_nr, _ = timed(args.steps, e2e=False)
-            no_rc = {"value": round(SEQ_LEN * world / (ms_nr / 1e3), 1), "unit": "tokens/s", "ms_per_step": round(ms_nr, 2),
+            no_rc = {"value": round(seq_len * dp / (ms_nr / 1e3), 1), "unit": "tokens/s", "ms_per_step": round(ms_nr, 2),
                      "max_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1)}
         except torch.OutOfMemoryError:
             no_rc = {"value": None, "note": "out of memory without recomputation"}
-        except Exception as ex:  # noqa: BLE001  (a side measurement must never take the headline line down with it)
+        except Exception as ex:  # noqa: BLE001
             no_rc = {"value": None, "note": f"{type(ex).__name__}: {str(ex)[:160]}"}
         inner.gradient_checkpointing = prev
-    if args.torch_profile:  # debugging aid, outside every timed region: per-kernel device time of one step on rank 0
+    nccl_ab = None
+    if fsdp and not args.skip_ab and not args.nccl_comm and ep == 1:
+        try:  # the same step on PyTorch's default NCCL all-gather / reduce-scatter (same process, same weights)
+            from veomni_b200.fsdp_comm import reinstall_fsdp_comm, uninstall_fsdp_comm
+
+            saved = uninstall_fsdp_comm(model)
+            for i in range(2):
+                step(resident[i % nbuf], i)
+            ms_nccl, _ = timed(args.steps, e2e=False)
+            reinstall_fsdp_comm(model, saved)
+            for i in range(1):
+                step(resident[i % nbuf], i)
+            ms_again, _ = timed(args.steps, e2e=False)
+            nccl_ab = {"ms_per_step_nccl_comm": round(ms_nccl, 2), "ms_per_step_b200_comm": round(ms_again, 2),
+                       "speedup": round(ms_nccl / ms_again, 4), "note": "same process, same weights; B200 comm re-timed right after the NCCL leg"}
+        except Exception as ex:  # noqa: BLE001
+            nccl_ab = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+    if args.torch_profile:  # debugging aid: per-kernel device time of one step on rank 0
         from torch.profiler import ProfilerActivity, profile
 
         dist.barrier()
@@ -252,16 +380,15 @@ def run_b200(args) -> None:
             torch.cuda.synchronize()
         if rank == 0:
             with open(args.torch_profile, "w") as fh:
-                fh.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+                fh.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=70, max_name_column_width=90))
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else {}
 
     if rank == 0:
         peaks = _peaks()
-        tokens = SEQ_LEN * world
+        tokens = seq_len * dp
         value = tokens / (ms_dev / 1e3)
-        fpt = flops_per_token(cfg, [SEQ_LEN])
-        fwd_flops = 4 * SEQ_LEN * SEQ_LEN * cfg.head_dim * cfg.num_attention_heads / 2  # causal fwd per launch
+        heads_local = cfg.num_attention_heads // sp
+        fwd_flops = 4 * seq_len * seq_len * cfg.head_dim * heads_local / 2  # causal fwd per launch
         # algorithmic FLOPs per launch: fwd = 2 matmuls, dQ = 1, dK+dV = 2 of the 5 backward matmuls
         kinfo = {"fwd": ("attn_fwd_tc_kernel (varlen causal attention forward, tcgen05)", fwd_flops),
                  "bwd_dkdv": ("attn_bwd_dkdv_tc_kernel (attention backward dK/dV, tcgen05)", fwd_flops * 2.5 * 0.6),
@@ -272,20 +399,30 @@ def run_b200(args) -> None:
         attn_flops = kinfo[dom][1]
         attn_avg_ms = sum(attn_ms) / max(1, len(attn_ms))
         achieved = attn_flops / (attn_avg_ms * 1e-3) / 1e12 if attn_ms else None
+        names = {"qwen3_8b": "Qwen3-8B FSDP2 bf16 seq_len 4096 training step (BASELINE configs[1])",
+                 "ulysses32k": f"Qwen3-8B FSDP2 + Ulysses SP{sp} bf16, one 32768-token sample per SP group (BASELINE configs[2])",
+                 "moe30b": f"Qwen3-30B-A3B FSDP2 + EP{ep} bf16 seq_len 4096, GroupGEMM path (BASELINE configs[3])"}
+        par = ("single GPU, no FSDP wrap (as the reference at world_size 1)" if not fsdp else
+               f"fsdp{dp * sp}" + (f" x ulysses{sp}" if sp > 1 else "") + (f" + ep{ep}" if ep > 1 else ""))
         out = {
-            "metric": METRIC, "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_dev, 2), "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC if wl == "qwen3_8b" else f"tokens/sec ({wl})", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "Qwen3-8B FSDP2 bf16 seq_len 4096 training step (BASELINE configs[1]): fwd+bwd with per-layer "
-                                   "gradient checkpointing, clip_grad_norm, fused AdamW; 1x4096-token packed sample per rank",
-                       "global_batch": world, "seq_len": SEQ_LEN, "parallelism": f"fsdp{world}", "layers": cfg.num_hidden_layers,
-                       "params_b": round(cfg.num_params() / 1e9, 3), "l2": "inputs (16 GB of bf16 weights per step) larger than L2",
-                       "fsdp_comm": "nccl" if args.nccl_comm else "veomni_b200 NVLink pull kernels",
-                       "optimizer": "veomni_b200 multi-tensor AdamW (experimental)" if args.b200_adamw else "torch.optim.AdamW(fused=True)",
+            "config": {"workload": names[wl] + ": fwd+bwd with per-layer gradient checkpointing (attention o/lse are kept across the "
+                                   "recompute instead of re-running the attention kernel — the reference recomputes it), clip_grad_norm, "
+                                   f"AdamW; one {seq_len}-token packed sample per data-parallel rank",
+                       "global_batch": dp, "seq_len": seq_len, "parallelism": par, "layers": cfg.num_hidden_layers,
+                       "params_b": round(cfg.num_params() / 1e9, 3) if wl != "moe30b" else 30.5,
+                       "l2": "inputs (>= 16 GB of bf16 weights per step) larger than L2",
+                       "fsdp_comm": ("none (1 GPU)" if not fsdp else "nccl" if args.nccl_comm else
+                                     f"veomni_b200 NVLink kernels: all-gather pull{' with fused copy-out' if not args.no_fuse_copy_out else ''}, "
+                                     f"reduce-scatter {args.rs_mode or 'push'} ({args.comm_ctas} CTAs)"),
+                       "reshard_after_forward": reshard if fsdp else None,
+                       "optimizer": "torch.optim.AdamW(fused=True)" if args.torch_adamw else
+                                    ("veomni_b200 multi-tensor AdamW" + (" on fp32 masters + bf16 model copy" if not fsdp else " on the fp32 shards")
+                                     + (", clip coefficient folded in" if fold_clip else "")),
                        "valid": args.layers == 0},
             "tokens_per_sec_per_gpu": round(value / world, 1),
-            "mfu_measured_peak": round(fpt * value / world / (peaks["bf16_tflops_sustained"] * 1e12), 4),
-            "mfu_2250": round(fpt * value / world / 2250e12, 4),
             "e2e": {"value": round(tokens / (ms_e2e / 1e3), 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e, 2)},
             "gpu_launches": int(launches),
@@ -295,17 +432,42 @@ def run_b200(args) -> None:
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16_tflops_sustained"], 4) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-                         # the same kernel at the same shape (profiles/r01_attn_bwd_*_tc_ts_ncu.txt, r01_attn_fwd_tc_v3_ncu.txt)
-                         "traffic": NCU_TRAFFIC_BYTES.get(dom), "traffic_source": "profiles/r01_attn_*_ncu.txt (ncu --set full)",
+                         # the same kernel at the same shape (profiles/r0*_attn_*_ncu.txt)
+                         "traffic": NCU_TRAFFIC_BYTES.get(dom) if (wl == "qwen3_8b") else None,
+                         "traffic_source": "profiles/r01_attn_*_ncu.txt (ncu --set full)",
                          "peak_source": f"{peaks['how']} (sustained cuBLAS bf16, kernel timed inside a long step)",
                          "avg_launch_ms": round(attn_avg_ms, 4), "launches_timed": len(attn_ms),
                          "algorithmic_flops_per_launch": attn_flops},
             "clocks": clocks, "loss": round(loss_dev, 4), "loss_e2e": round(loss_e2e, 4), "max_mem_gb": round(mem_gb, 1),
         }
+        if wl != "moe30b":
+            fpt = flops_per_token(cfg, [seq_len])
+            out["mfu_measured_peak"] = round(fpt * value / world / (peaks["bf16_tflops_sustained"] * 1e12), 4)
+            out["mfu_2250"] = round(fpt * value / world / 2250e12, 4)
+        if comm_stats:
+            comm = {}
+            for tag, st in comm_stats.items():
+                per_step_ms = st["ms"] / max(1, args.steps)
+                ent = {"launches_per_step": st["launches"] // max(1, args.steps), "busy_ms_per_step": round(per_step_ms, 2)}
+                if tag == "group_gemm":
+                    ent["achieved_tflops"] = round(st["rate"] / 1e12, 1)
+                    ent["frac_of_peak"] = round(st["rate"] / 1e12 / peaks["bf16_tflops_sustained"], 3)
+                else:
+                    ent["nvlink_in_GBps"] = round(st["rate"] / 1e9, 1)
+                    ent["frac_of_900"] = round(st["rate"] / 1e9 / 900.0, 3)
+                comm[tag] = ent
+            out["comm"] = comm
+        if parity is not None:
+            out["parity"] = parity
+        if nccl_ab is not None:
+            out["nccl_ab"] = nccl_ab
         if no_rc is not None:
             out["no_recompute"] = no_rc
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(sample_tokens=256, iters=1, threads=None)
+            try:
+                out["cpu_baseline"] = cpu_sample(steps=2, warmup=1, budget_s=40.0)
+            except Exception as ex:  # noqa: BLE001
+                out["cpu_baseline"] = {"value": None, "error": f"{type(ex).__name__}: {str(ex)[:160]}"}
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()
@@ -317,12 +479,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="qwen3_8b", choices=["qwen3_8b", "ulysses32k", "moe30b"])
     ap.add_argument("--layers", type=int, default=0, help="debug only: fewer layers (marks the line invalid)")
     ap.add_argument("--nccl-comm", action="store_true", help="debug: PyTorch's default NCCL FSDP2 collectives")
     ap.add_argument("--comm-ctas", type=int, default=32)
+    ap.add_argument("--rs-mode", default=None, choices=["push", "pull", "f32"], help="reduce-scatter variant (default push: copy-in fused)")
+    ap.add_argument("--no-fuse-copy-out", action="store_true", help="debug: all-gather into the buffer + torch split_with_sizes_copy")
+    ap.add_argument("--reshard", type=int, default=0, help="FSDP2 reshard_after_forward (default 0: the bf16 parameters stay "
+                                                            "gathered between forward and backward — 16 GB of the 180 GB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--b200-adamw", action="store_true", help="experimental: veomni_b200.optim.B200AdamW instead of torch's fused AdamW")
+    ap.add_argument("--torch-adamw", action="store_true", help="debug: torch.optim.AdamW(fused=True) instead of the veomni_b200 kernel")
     ap.add_argument("--skip-no-recompute", action="store_true", help="skip the extra no-recomputation measurement")
+    ap.add_argument("--skip-parity", action="store_true", help="skip the multi-GPU parity stage")
+    ap.add_argument("--skip-ab", action="store_true", help="skip the NCCL-comm A/B side measurement")
     ap.add_argument("--torch-profile", default="", help="debug: write a torch.profiler kernel table of one extra step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -120,15 +120,18 @@ int vb200_multi_sumsq(const void* const* ptrs_dev, const int64_t* numels_dev, in
 int vb200_multi_scale(void* const* ptrs_dev, const int64_t* numels_dev, int32_t n_entries, int32_t dtype,
                       const float* coef_dev, void* stream);
 
-/* AdamW step on fp32 parameters / gradients / moments over a device table of entries (SURVEY.md §8(f)4 "next":
- * the reference builds torch.optim.AdamW(fused=True), veomni/optim/optimizer.py:261-328).  Same arithmetic as
- * PyTorch's fused kernel (ADAMW mode, no amsgrad / maximize); bias_correction1 = 1 - beta1^step,
- * bias_correction2_sqrt = sqrt(1 - beta2^step), computed by the caller.  grad_scale_dev (optional device scalar)
- * multiplies every gradient first.  EXPERIMENTAL until validated on hardware.                        */
+/* AdamW step over a device table of entries (the reference builds torch.optim.AdamW(fused=True),
+ * veomni/optim/optimizer.py:261-328).  Same arithmetic as PyTorch's fused kernel (ADAMW mode, no amsgrad / maximize) on
+ * fp32 parameters and moments; gradients fp32 (grad_dtype 1) or bf16 (0); bias_correction1 = 1 - beta1^step,
+ * bias_correction2_sqrt = sqrt(1 - beta2^step), computed by the caller.  grad_scale_dev (optional device scalar, e.g.
+ * the gradient-clip coefficient) multiplies every gradient first.  lp_params_dev (optional): a second pointer table —
+ * the updated parameter is also stored there rounded to bf16 (master-weight training without FSDP: the world_size-1
+ * path of build_parallelize_model, veomni/distributed/torch_parallelize.py:438-443,465).                              */
 int vb200_multi_adamw(void* const* params_dev, const void* const* grads_dev, void* const* exp_avgs_dev,
-                      void* const* exp_avg_sqs_dev, const int64_t* numels_dev, int32_t n_entries, float lr, float beta1,
-                      float beta2, float eps, float weight_decay, float bias_correction1,
-                      float bias_correction2_sqrt, const float* grad_scale_dev, void* stream);
+                      void* const* exp_avg_sqs_dev, void* const* lp_params_dev, const int64_t* numels_dev,
+                      int32_t n_entries, int32_t grad_dtype, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, float bias_correction1, float bias_correction2_sqrt,
+                      const float* grad_scale_dev, void* stream);
 
 /* ---- softmax cross-entropy over the vocabulary ------------------------------------------
  * Replaces the arithmetic of eager_cross_entropy -> transformers fixed_cross_entropy
@@ -234,6 +237,21 @@ int vb200_reduce_scatter_bf16(void* comm, int32_t channel, int64_t region_offset
  * shards cast into the bf16 all-gather input in one pass.                                            */
 int vb200_fsdp_pack_bf16(const int64_t* desc, int32_t n, int32_t world, int64_t row_elems, void* out,
                          int32_t src_dtype, void* stream);
+/* FSDP2 unit all-gather with the copy-out fused in: replaces DefaultAllGather.__call__ (:81-95) AND the
+ * fsdp::split_with_sizes_copy of foreach_all_gather_copy_out (:196-212, :346-412). As for vb200_allgather, rank p's
+ * shard row sits at region_offset + p*shard_bytes of its own region; table: host array of n x {byte offset of the
+ * parameter inside a shard row, bytes of one rank's shard of it, destination pointer}: rank p's piece of parameter i
+ * is pulled over NVLink straight into dst_i + p*bytes_i (the parameter's unsharded tensor, any local memory).       */
+int vb200_allgather_scatter(void* comm, int32_t channel, int64_t region_offset, int64_t shard_bytes,
+                            const int64_t* table, int32_t n, int32_t num_ctas, void* stream);
+/* FSDP2 unit reduce-scatter with the copy-in fused in: replaces foreach_reduce_scatter_copy_in -> torch._chunk_cat
+ * (:667-675), DefaultReduceScatter.__call__ (:116-131) and the divide (:701-759) for bf16 gradients reduced in fp32.
+ * desc: host array of n x {gradient pointer (bf16, contiguous, local), numel, chunk elements = ceil(dim0/world)*inner};
+ * row_elems = sum of chunks. Chunk p of every gradient (dim-0 zero-padded) is pushed to rank p's staging buffer
+ * [world, row_elems] bf16 at region_offset of its region (slot = source rank); then
+ * out[i] = scale * sum_{s=0..N-1} staging[s][i] in rank order, fp32.                                               */
+int vb200_reduce_scatter_push_bf16(void* comm, int32_t channel, int64_t region_offset, const int64_t* desc, int32_t n,
+                                   int64_t row_elems, float scale, float* out, int32_t num_ctas, void* stream);
 /* Strided chunk exchange, replaces dist.all_to_all_single + the reshape/cat copies of
  * _all_to_all_single (veomni/distributed/sequence_parallel/ulysses.py:86-122).
  * desc: n_desc x 8 int64 = {src_off, src_rank_stride, src_row_stride, dst pointer,

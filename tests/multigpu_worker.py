@@ -84,6 +84,30 @@ def test_reduce_scatter_bf16(symm, rank, world, dev):
     symm.check()
 
 
+def test_reduce_scatter_push_oracle(symm, rank, world, dev):
+    """Fused copy-in reduce-scatter == oracle: FSDP2's chunk_cat copy-in + reduce-scatter in fixed rank order + divide."""
+    from veomni_b200.fsdp_comm import pack_plan
+
+    shapes = [(64, 24), (9, 5), (33,), (128, 16)]
+    g = torch.Generator(device="cpu").manual_seed(17 * rank + 1)
+    grads = [torch.randn(*s, generator=g).to(torch.bfloat16).to(dev) for s in shapes]
+    plan, row = pack_plan(shapes, world)
+    staging = symm.empty((row * world,), torch.float32, arena="fsdp_rs")
+    out = torch.empty(row, dtype=torch.float32, device=dev)
+    desc = []
+    for t, (numel, chunk, _off) in zip(grads, plan):
+        desc += [t.data_ptr(), numel, chunk]
+    symm.reduce_scatter_push_bf16(staging, desc, row, out, 1.0 / world, 1)
+    # oracle input: every rank's fp32 chunk_cat buffer (what torch's copy-in produces), gathered with NCCL
+    mine = torch.empty(world, row, dtype=torch.float32, device=dev)
+    torch._chunk_cat([t.float() for t in grads], dim=0, num_chunks=world, out=mine)
+    xs = gather_all(mine.flatten())
+    ref = o_comm.fsdp_reduce_scatter([t.cpu() for t in xs], torch.float32, None)[rank] * (1.0 / world)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref), f"push reduce-scatter vs oracle: {(out.cpu() - ref).abs().max()}"
+    symm.check()
+
+
 def test_ulysses(rank, world, dev):
     from veomni_b200 import ulysses as U
 
@@ -401,8 +425,18 @@ def main():
     stage("reduce_scatter (generic instantiation)", test_reduce_scatter, symm, rank, world, dev)
     stage("reduce_scatter bf16 pull (generic instantiation)", test_reduce_scatter_bf16, symm, rank, world, dev)
     os.environ.pop("VB200_RS_GENERIC")
+    from veomni_b200 import selfcheck
+
+    stage("all-gather with fused copy-out (oracle-free self-check)", selfcheck.check_allgather_scatter, symm, dev)
+    stage("reduce-scatter with fused copy-in (oracle-free self-check)", selfcheck.check_reduce_scatter_push, symm, dev)
+    stage("reduce-scatter with fused copy-in vs the fixed-order oracle", test_reduce_scatter_push_oracle, symm, rank, world, dev)
+    os.environ["VB200_RS_GENERIC"] = "1"
+    stage("reduce-scatter with fused copy-in (generic instantiation)", selfcheck.check_reduce_scatter_push, symm, dev)
+    os.environ.pop("VB200_RS_GENERIC")
     stage("ulysses", test_ulysses, rank, world, dev)
     stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
+    stage("fsdp2 custom comm: every mode, ragged shapes, divide factor (self-check)", selfcheck.check_fsdp, dev, world)
+    stage("EP dispatch/combine (self-check)", selfcheck.check_ep_dispatch, symm, dev)
     stage("expert parallel dispatch/combine", test_ep, rank, world, dev)
     stage("ulysses SP through the model (reference fixture)", test_ulysses_model, rank, world, dev)
     stage("expert parallel through the Qwen3-MoE caller", test_ep_model, rank, world, dev)

@@ -238,7 +238,6 @@ def test_attention_tcgen05_operand_variants_agree(cuda_dev):
         A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS, A.BWD_PP = old
 
 
-@pytest.mark.skipif(os.environ.get("VB200_EXPERIMENTAL", "0") != "1", reason="experimental kernel variant: set VB200_EXPERIMENTAL=1")
 def test_attention_tcgen05_forward_eight_softmax_warps(cuda_dev):
     """attn_fwd_tc_kernel<W8> (two warps per row, half the columns each) against the default four-warp kernel: the row
     maxima, the lazy-rescale decisions and every exponential are the same numbers, only the row sums are added in a

@@ -16,7 +16,9 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("tokens/sec") and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["value"] > 0 and d["config"]["workload"].startswith("Qwen3-8B FSDP2 bf16 seq_len 4096")
+    assert d["value"] > 0 and d["config"]["workload"].startswith("Qwen3-8B bf16 seq_len 4096")
+    # the timed step is the bounded sample itself, really executed: value and ms_per_step describe the same measurement
+    assert abs(d["value"] - d["config"]["sample_tokens"] / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-2
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -220,7 +220,6 @@ def test_clip_grad_norm_matches_torch(cuda_dev):
         torch.testing.assert_close(a.grad, b.grad, atol=1e-12, rtol=2e-6)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("VB200_EXPERIMENTAL", "0") != "1", reason="experimental: set VB200_EXPERIMENTAL=1")
 def test_b200_adamw_matches_torch_fused(cuda_dev):
     """B200AdamW against torch.optim.AdamW(fused=True): same hyper-parameters, 5 steps, ragged shapes (multi-entry tensors,
     unaligned views); parameters within 2e-6 relative (fp32, different but equivalent operation order)."""
@@ -250,7 +249,35 @@ def test_b200_adamw_matches_torch_fused(cuda_dev):
         torch.testing.assert_close(b, a, atol=1e-7, rtol=2e-6)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("VB200_EXPERIMENTAL", "0") != "1", reason="experimental: set VB200_EXPERIMENTAL=1")
+def test_b200_adamw_master_weights_bf16_grads(cuda_dev):
+    """master_weights=True (the world_size-1 path): bf16 model copy + bf16 gradients, fp32 master / moments inside the
+    optimizer. Reference: torch.optim.AdamW(fused=True) on fp32 copies fed the same bf16 gradient values (bf16 -> fp32 is
+    exact); the bf16 model parameter must be the fp32 master rounded to nearest-even, bit for bit."""
+    from veomni_b200.optim import B200AdamW
+
+    torch.manual_seed(1)
+    shapes = [(5,), (257, 129), ((1 << 20) + 3,), (2048, 1024)]
+    ref = [torch.nn.Parameter(torch.randn(*s, device=cuda_dev)) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    kw = dict(lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    o_ref, o_mine = torch.optim.AdamW(ref, fused=True, **kw), B200AdamW(mine, master_weights=True, **kw)
+    assert all(p.dtype == torch.bfloat16 for p in mine)
+    for a, b in zip(ref, mine):
+        assert torch.equal(b.data, a.data.to(torch.bfloat16))
+    for step in range(4):
+        coef = torch.tensor(0.5 if step == 3 else 1.0, device=cuda_dev)
+        for a, b in zip(ref, mine):
+            g = torch.randn_like(a).to(torch.bfloat16)
+            a.grad, b.grad = g.float() * coef, g.clone()
+        o_ref.step()
+        o_mine.step(grad_scale=coef if step == 3 else None)
+    for a, b in zip(ref, mine):
+        master = o_mine.state[b]["master"]
+        torch.testing.assert_close(master, a.data, atol=1e-7, rtol=2e-6)
+        assert torch.equal(b.data, master.to(torch.bfloat16))
+        assert o_mine.state[b]["exp_avg"].dtype == torch.float32
+
+
 @pytest.mark.parametrize("rows,cols", [(1, 1024), (37, 2048), (4096, 4096), (65, 5120), (9, 8192)])
 def test_fused_add_rms_norm_equals_add_then_norm(cuda_dev, rows, cols):
     """fused_add_rms_norm == (residual + x in bf16, then rms_norm): forward bit-exact (same rounding points), backward

@@ -193,3 +193,43 @@ def test_sp_loss_reduce_matches_reference_world2_gloo():
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_sp_loss_worker, args=(2, os.path.join(d, "store"), d), nprocs=2, join=True)
         assert all(torch.load(os.path.join(d, f"ok{r}.pt")) for r in range(2))
+
+
+def test_ep_plan_chunks_matches_the_loop_restatement():
+    """veomni_b200.ep.plan_chunks (vectorised) == the per-(expert, source) loops that define the EP exchange geometry
+    (moe_layer.py:30-69 preprocess + moe_utils.py:81-99 sort_chunks_by_idxs), for every rank, with empty blocks."""
+    import torch
+
+    from veomni_b200.ep import plan_chunks
+
+    g = torch.Generator().manual_seed(0)
+    for ep, el in ((2, 4), (4, 3), (8, 16)):
+        E = ep * el
+        counts = torch.randint(0, 7, (ep, E), generator=g, dtype=torch.int64)
+        counts[0, 1] = 0
+        counts[:, E - 1] = 0  # an expert nobody picked
+        row = 64
+        excl = torch.cumsum(counts, dim=1) - counts
+        for r in range(ep):
+            ins, outs, total, cumsum, fwd, bwd = plan_chunks(counts, r, row)
+            assert ins == counts[r].view(ep, el).sum(1).tolist()
+            assert outs == counts[:, r * el:(r + 1) * el].sum(1).tolist()
+            exp_fwd, dst = [], 0
+            for le in range(el):
+                e = r * el + le
+                for s in range(ep):
+                    n = int(counts[s, e])
+                    exp_fwd.append([int(excl[s, e]) * row, dst * row, n * row, s])
+                    dst += n
+            assert total == dst
+            assert fwd.tolist() == exp_fwd
+            assert cumsum.tolist() == torch.cumsum(counts[:, r * el:(r + 1) * el].sum(0), 0).tolist()
+            exp_bwd = []
+            tot = counts.sum(0)
+            for p in range(ep):
+                base = 0
+                for le in range(el):
+                    e = p * el + le
+                    exp_bwd.append([(base + int(counts[:r, e].sum())) * row, int(excl[r, e]) * row, int(counts[r, e]) * row, p])
+                    base += int(tot[e])
+            assert bwd.tolist() == exp_bwd

@@ -1,4 +1,5 @@
 """Additional microbenchmarks (attention, comm, MoE); imported lazily by tools/microbench.py."""
+import json
 import os
 
 import torch
@@ -28,15 +29,16 @@ def bench_attention(dev, iters):
                    flops=flops_fwd)
     except Exception as ex:  # noqa: BLE001
         print({"attn_fwd_tcgen05": str(ex)})
-    if os.environ.get("VB200_EXPERIMENTAL", "0") == "1":
-        A.FWD_IMPL, A.FWD_W8 = "tc", True
+    old_w8 = A.FWD_W8
+    for w8 in (False, True):
+        A.FWD_IMPL, A.FWD_W8 = "tc", w8
         try:
             with torch.no_grad():
-                report("attn_fwd_tcgen05 (8 softmax warps, experimental)[4096,32/8,128,causal]",
+                report(f"attn_fwd_tcgen05 (W8={w8})[4096,32/8,128,causal]",
                        time_fn(lambda q, k, v: flash_attn_varlen(q, k, v, cu, T), sets, iters), flops=flops_fwd)
         except Exception as ex:  # noqa: BLE001
             print({"attn_fwd_tcgen05_w8": str(ex)})
-        A.FWD_W8 = False
+    A.FWD_W8 = old_w8
     A.FWD_IMPL = old
     gsets = [tuple(t.clone().requires_grad_(True) for t in s) for s in sets]
     do = torch.randn(T, Hq, D, device=dev, dtype=BF)
@@ -116,6 +118,27 @@ def bench_moe(dev, iters):
         hs_g.grad = w1_g.grad = w2_g.grad = rw_g.grad = None
 
     report("fused_moe fwd+bwd[Qwen3-30B-A3B layer, T=4096]", time_fn(fb, [()], iters), flops=3 * 2 * T * K * 3 * I * H)
+    try:  # the existing Blackwell kernel the reference can call (veomni/ops/kernels/moe/quack_gemm.py:28,88-161): quack-kernels
+        from quack.gemm_interface import gemm as qgemm
+
+        cu = torch.zeros(E + 1, dtype=torch.int32, device=dev)
+        cu[1:] = cumsum.int()
+        w1t, w2t = w1.transpose(1, 2), w2.transpose(1, 2)
+        with torch.no_grad():
+            ref = qgemm(x, w1t, cu_seqlens_m=cu)
+            mine = group_gemm_same_nk(x, w1, cumsum, transpose_b=True)
+            print(json.dumps({"quack_vs_vb200_fc1_maxabs": float((ref.float() - mine.float()).abs().max()),
+                              "ref_absmax": float(ref.float().abs().max())}), flush=True)
+            report("(lib) quack gemm fc1 cu_seqlens_m[32768x2048 -> 1536]", time_fn(lambda: qgemm(x, w1t, cu_seqlens_m=cu), [()], iters),
+                   flops=2 * T * K * 2 * I * H)
+            report("(lib) quack gemm fc2 cu_seqlens_m[32768x768 -> 2048]", time_fn(lambda: qgemm(act, w2t, cu_seqlens_m=cu), [()], iters),
+                   flops=2 * T * K * I * H)
+            report("(lib) quack gemm dgrad fc1 cu_seqlens_m[32768x1536 -> 2048]", time_fn(lambda: qgemm(a, w1, cu_seqlens_m=cu), [()], iters),
+                   flops=2 * T * K * 2 * I * H)
+            report("(lib) quack gemm wgrad fc1 cu_seqlens_k[128 x 1536x2048]", time_fn(lambda: qgemm(a.T, x, cu_seqlens_k=cu), [()], iters),
+                   flops=2 * T * K * 2 * I * H)
+    except Exception as ex:  # noqa: BLE001
+        print(json.dumps({"quack": f"{type(ex).__name__}: {str(ex)[:300]}"}), flush=True)
     try:  # library reference: cuBLAS dense GEMM of the same FLOPs
         a2 = torch.randn(T * K, H, device=dev, dtype=BF)
         b2 = torch.randn(2 * I, H, device=dev, dtype=BF)

@@ -49,7 +49,7 @@ SIGNATURES = {
     "vb200_multi_scale": (c_int, [_P, _P, _I32, _I32, _P, _P]),
     "vb200_add_rmsnorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _I64, _I64, _F, _P]),
     "vb200_rmsnorm_bwd_add": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
-    "vb200_multi_adamw": (c_int, [_P, _P, _P, _P, _P, _I32, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
+    "vb200_multi_adamw": (c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
     "vb200_cross_entropy": (c_int, [_P, _I32, _I64, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _I64, _F, _P, _P, _P]),
     "vb200_count_valid_labels": (c_int, [_P, _I64, _I64, _P, _P]),
     "vb200_swiglu_fwd": (c_int, [_P, _P, _P, _I64, _I64, _I64, _I64, _P]),
@@ -77,6 +77,8 @@ SIGNATURES = {
     "vb200_allgather": (c_int, [_P, _I32, _I64, _I64, _I32, _P]),
     "vb200_reduce_scatter_f32": (c_int, [_P, _I32, _I64, _I64, _F, _P, _I32, _P]),
     "vb200_reduce_scatter_bf16": (c_int, [_P, _I32, _I64, _I64, _F, _P, _I32, _P]),
+    "vb200_allgather_scatter": (c_int, [_P, _I32, _I64, _I64, _P, _I32, _I32, _P]),
+    "vb200_reduce_scatter_push_bf16": (c_int, [_P, _I32, _I64, _P, _I32, _I64, _F, _P, _I32, _P]),
     "vb200_fsdp_pack_bf16": (c_int, [_P, _I32, _I32, _I64, _P, _I32, _P]),
     "vb200_all_to_all": (c_int, [_P, _I32, _I64, _I32, _P, _I32, _P]),
     "vb200_chunk_pull": (c_int, [_P, _I32, _I64, _P, _I32, _P, _I32, _P]),

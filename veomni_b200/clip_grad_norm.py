@@ -127,7 +127,10 @@ def _reduce_group(params, norm_type: float, groups) -> torch.Tensor:
 
 @torch.no_grad()
 def clip_grad_norm(model: torch.nn.Module, max_norm: float, norm_type: float = 2.0, error_if_nonfinite: bool = False,
-                   foreach: bool | None = None) -> torch.Tensor:
+                   foreach: bool | None = None, return_coef: bool = False):
+    """Same contract as the reference. ``return_coef=True`` (ours): the gradients are left untouched and
+    ``(total_norm, coef)`` is returned, ``coef`` a device scalar to hand to ``B200AdamW.step(grad_scale=coef)`` — the
+    scaling pass over every gradient folds into the optimizer kernel. Only the plain FSDP2 L2 path supports it."""
     ps = get_parallel_state()
     expert, dense = [], []
     for p in model.parameters():
@@ -138,6 +141,8 @@ def clip_grad_norm(model: torch.nn.Module, max_norm: float, norm_type: float = 2
     if not expert:
         grads = [_local(p.grad) for p in dense]
         if not _kernel_path_ok(grads, norm_type):
+            if return_coef:
+                raise NotImplementedError("clip_grad_norm(return_coef=True) needs contiguous CUDA fp32 / bf16 gradients and the L2 norm")
             total = torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.grad is not None], max_norm,
                                                    norm_type=norm_type, error_if_nonfinite=error_if_nonfinite, foreach=foreach)
             return total.full_tensor() if isinstance(total, DTensor) else total
@@ -155,8 +160,13 @@ def clip_grad_norm(model: torch.nn.Module, max_norm: float, norm_type: float = 2
         total = total_sq.sqrt()
         if error_if_nonfinite and not torch.isfinite(total):
             raise RuntimeError(f"The total norm of order {norm_type} for gradients is non-finite")
-        multi_scale_(grads, torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        if return_coef:
+            return total, coef
+        multi_scale_(grads, coef)
         return total
+    if return_coef:
+        raise NotImplementedError("clip_grad_norm(return_coef=True) covers the non-EP L2 path only")
     fsdp_group = ps.fsdp_group if ps.device_mesh is not None and dist.is_initialized() else None
     ep_fsdp_group = ps.ep_fsdp_device_mesh["ep_fsdp"].get_group() if ps.ep_fsdp_device_mesh is not None else None
     d = _reduce_group(dense, norm_type, [fsdp_group])

@@ -153,14 +153,18 @@ struct AdamWArgs {
     float lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2_sqrt;
 };
 
+// G = gradient type (float or bf16). LP: also write the updated parameter, rounded to bf16, to a second table
+// ("master weights": the fp32 parameter lives in the optimizer, the model computes on the bf16 copy).
+template <typename G, bool LP>
 __global__ void __launch_bounds__(kMtThreads)
 multi_adamw_kernel(void* const* __restrict__ params, const void* const* __restrict__ grads, void* const* __restrict__ exp_avgs,
-                   void* const* __restrict__ exp_avg_sqs, const int64_t* __restrict__ numels, AdamWArgs a,
-                   const float* __restrict__ grad_scale) {
+                   void* const* __restrict__ exp_avg_sqs, void* const* __restrict__ lp_params,
+                   const int64_t* __restrict__ numels, AdamWArgs a, const float* __restrict__ grad_scale) {
     float* p = reinterpret_cast<float*>(params[blockIdx.x]);
-    const float* g = reinterpret_cast<const float*>(grads[blockIdx.x]);
+    const G* g = reinterpret_cast<const G*>(grads[blockIdx.x]);
     float* m = reinterpret_cast<float*>(exp_avgs[blockIdx.x]);
     float* v = reinterpret_cast<float*>(exp_avg_sqs[blockIdx.x]);
+    __nv_bfloat16* lp = LP ? reinterpret_cast<__nv_bfloat16*>(lp_params[blockIdx.x]) : nullptr;
     const int64_t n = numels[blockIdx.x];
     const float gs = grad_scale ? *grad_scale : 1.0f;
     const float step_size = a.lr / a.bias_correction1, decay = 1.0f - a.lr * a.weight_decay;
@@ -172,27 +176,53 @@ multi_adamw_kernel(void* const* __restrict__ params, const void* const* __restri
         vv = fmaf(a.beta2, vv, omb2 * gg * gg);
         pp -= step_size * mm / (sqrtf(vv) * inv_bc2s + a.eps);
     };
+    auto gload = [&](int64_t i) -> float {
+        if constexpr (sizeof(G) == 4) return reinterpret_cast<const float*>(g)[i];
+        else return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(g)[i]);
+    };
     const int64_t tid = (int64_t)blockIdx.y * kMtThreads + threadIdx.x;
     const int64_t nthr = (int64_t)kMtBlocks * kMtThreads;
-    // all four arrays of an entry share their 16-byte phase only if the caller guarantees it (entries are cut at
+    // all arrays of an entry share their 16-byte phase only if the caller guarantees it (entries are cut at
     // multiples of 2^20 elements from 256-byte aligned allocations); otherwise the scalar path runs
-    const bool aligned = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+    bool aligned = ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15) == 0) && (((uintptr_t)g & (sizeof(G) == 4 ? 15 : 7)) == 0);
+    if (LP) aligned = aligned && (((uintptr_t)lp & 7) == 0);
     if (aligned) {
         const int64_t nvec = n >> 2;
         for (int64_t i = tid; i < nvec; i += nthr) {
             float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
-            const uint4 gr = ldg_stream(reinterpret_cast<const uint4*>(g) + i);
-            upd(pv.x, __uint_as_float(gr.x), mv.x, vv.x);
-            upd(pv.y, __uint_as_float(gr.y), mv.y, vv.y);
-            upd(pv.z, __uint_as_float(gr.z), mv.z, vv.z);
-            upd(pv.w, __uint_as_float(gr.w), mv.w, vv.w);
+            float g0, g1, g2, g3;
+            if constexpr (sizeof(G) == 4) {
+                const uint4 gr = ldg_stream(reinterpret_cast<const uint4*>(g) + i);
+                g0 = __uint_as_float(gr.x); g1 = __uint_as_float(gr.y); g2 = __uint_as_float(gr.z); g3 = __uint_as_float(gr.w);
+            } else {
+                uint2 gr;
+                asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(gr.x), "=r"(gr.y) : "l"(reinterpret_cast<const uint2*>(g) + i));
+                const float2 a0 = bf2_to_f2(gr.x), a1 = bf2_to_f2(gr.y);
+                g0 = a0.x; g1 = a0.y; g2 = a1.x; g3 = a1.y;
+            }
+            upd(pv.x, g0, mv.x, vv.x);
+            upd(pv.y, g1, mv.y, vv.y);
+            upd(pv.z, g2, mv.z, vv.z);
+            upd(pv.w, g3, mv.w, vv.w);
             reinterpret_cast<float4*>(p)[i] = pv;
             reinterpret_cast<float4*>(m)[i] = mv;
             reinterpret_cast<float4*>(v)[i] = vv;
+            if (LP) {
+                uint2 o;
+                o.x = f2_to_bf2(pv.x, pv.y);
+                o.y = f2_to_bf2(pv.z, pv.w);
+                reinterpret_cast<uint2*>(lp)[i] = o;
+            }
         }
-        for (int64_t i = (nvec << 2) + tid; i < n; i += nthr) upd(p[i], g[i], m[i], v[i]);
+        for (int64_t i = (nvec << 2) + tid; i < n; i += nthr) {
+            upd(p[i], gload(i), m[i], v[i]);
+            if (LP) lp[i] = __float2bfloat16_rn(p[i]);
+        }
     } else {
-        for (int64_t i = tid; i < n; i += nthr) upd(p[i], g[i], m[i], v[i]);
+        for (int64_t i = tid; i < n; i += nthr) {
+            upd(p[i], gload(i), m[i], v[i]);
+            if (LP) lp[i] = __float2bfloat16_rn(p[i]);
+        }
     }
 }
 
@@ -235,18 +265,26 @@ extern "C" int vb200_multi_scale(void* const* ptrs_dev, const int64_t* numels_de
 }
 
 extern "C" int vb200_multi_adamw(void* const* params_dev, const void* const* grads_dev, void* const* exp_avgs_dev,
-                                 void* const* exp_avg_sqs_dev, const int64_t* numels_dev, int32_t n_entries, float lr, float beta1,
-                                 float beta2, float eps, float weight_decay, float bias_correction1,
-                                 float bias_correction2_sqrt, const float* grad_scale_dev, void* stream) {
+                                 void* const* exp_avg_sqs_dev, void* const* lp_params_dev, const int64_t* numels_dev,
+                                 int32_t n_entries, int32_t grad_dtype, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, float bias_correction1, float bias_correction2_sqrt,
+                                 const float* grad_scale_dev, void* stream) {
     if (n_entries == 0) return VB200_OK;
     if (n_entries < 0 || !params_dev || !grads_dev || !exp_avgs_dev || !exp_avg_sqs_dev || !numels_dev)
         return vb200_set_error(VB200_EINVAL, "multi_adamw: bad arguments");
+    if (grad_dtype != 0 && grad_dtype != 1) return vb200_set_error(VB200_EINVAL, "multi_adamw: grad_dtype must be 0 (bf16) or 1 (f32)");
     if (!(bias_correction1 > 0.f) || !(bias_correction2_sqrt > 0.f))
         return vb200_set_error(VB200_EINVAL, "multi_adamw: bias corrections must be positive (step >= 1)");
     AdamWArgs a{lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2_sqrt};
     dim3 grid(n_entries, kMtBlocks);
-    multi_adamw_kernel<<<grid, kMtThreads, 0, (cudaStream_t)stream>>>(params_dev, grads_dev, exp_avgs_dev, exp_avg_sqs_dev, numels_dev, a,
-                                                                       grad_scale_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+#define VB_ADAMW(G, LP) multi_adamw_kernel<G, LP><<<grid, kMtThreads, 0, st>>>(params_dev, grads_dev, exp_avgs_dev, exp_avg_sqs_dev, lp_params_dev, numels_dev, a, grad_scale_dev)
+    if (grad_dtype == 1) {
+        if (lp_params_dev) VB_ADAMW(float, true); else VB_ADAMW(float, false);
+    } else {
+        if (lp_params_dev) VB_ADAMW(__nv_bfloat16, true); else VB_ADAMW(__nv_bfloat16, false);
+    }
+#undef VB_ADAMW
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;

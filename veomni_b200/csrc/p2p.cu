@@ -40,8 +40,11 @@ struct CommDev {
     int rank, world;
     uint8_t* data[kMaxWorld];   // peers' symmetric data regions, mapped locally
     uint64_t* sig[kMaxWorld];   // peers' signal pads
-    uint32_t* state;            // local: epoch[kMaxChannels], counter[kMaxChannels], error
+    uint32_t* state;            // local: epoch[kMaxChannels], counter[kMaxChannels], error (+3 pad), counter2[kMaxChannels]
 };
+constexpr int kStateError = 2 * kMaxChannels;
+constexpr int kStateCounter2 = 2 * kMaxChannels + 4;
+constexpr int kStateWords = 3 * kMaxChannels + 4;
 
 struct CommHost {
     CommDev dev;
@@ -76,7 +79,7 @@ __device__ __forceinline__ void wait_peers(const CommDev& c, int ch, int kind, u
         while ((int32_t)((uint32_t)(v = ld_acquire_sys(f)) - e) < 0) {
             __nanosleep(40);
             if (clock64() - t0 > kSpinLimit) {
-                atomicExch(c.state + 2 * kMaxChannels, 1u);
+                atomicExch(c.state + kStateError, 1u);
                 break;
             }
         }
@@ -436,6 +439,16 @@ all_to_all_kernel(CommDev c, int ch, int64_t off, A2AArgs args) {
     if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
 }
 
+// largest i in [0, n) with prefix[i] <= v (prefix[0] = 0, prefix[n] > v; zero-sized entries are skipped)
+__device__ __forceinline__ int find_segment(const int64_t* prefix, int n, int64_t v) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // Variable-size chunk pull (EP dispatch / combine): a device-side list of up to `nchunks` copies
 // {peer, src_off (bytes in the peer's region), dst_off (bytes from dst), bytes}; chunk sizes are
 // multiples of 16 bytes. One CTA-group sweeps each chunk; the list itself lives in device memory so
@@ -445,31 +458,324 @@ struct ChunkDesc {
     int32_t peer, pad;
 };
 
+constexpr int kChunkSmem = 1024;  // chunk lists up to this length are swept as ONE flattened index space
+
 __global__ void __launch_bounds__(512)
 chunk_pull_kernel(CommDev c, int ch, int64_t off, const ChunkDesc* __restrict__ chunks, int nchunks,
                   uint8_t* __restrict__ dst) {
     __shared__ int64_t peer_off[kMaxWorld];
+    __shared__ int64_t s_prefix[kChunkSmem + 1];  // 16-byte vectors before chunk k
     const uint32_t e = c.state[ch] + 1;
     if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
+    const bool flat = nchunks <= kChunkSmem;
+    if (flat) {
+        // exclusive prefix of the chunk sizes (block-wide: 2 chunks per thread, then a serial pass over 32 warp totals)
+        __shared__ int64_t warp_tot[16];
+        const int t = threadIdx.x;
+        const int64_t a0 = 2 * t < nchunks ? (chunks[2 * t].bytes >> 4) : 0;
+        const int64_t a1 = 2 * t + 1 < nchunks ? (chunks[2 * t + 1].bytes >> 4) : 0;
+        int64_t v = a0 + a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t u = __shfl_up_sync(0xffffffffu, v, o);
+            if ((t & 31) >= o) v += u;
+        }
+        if ((t & 31) == 31) warp_tot[t >> 5] = v;
+        __syncthreads();
+        int64_t base = 0;
+        for (int w = 0; w < (t >> 5); ++w) base += warp_tot[w];
+        const int64_t incl = base + v;  // inclusive over pairs
+        if (2 * t < kChunkSmem) {
+            s_prefix[2 * t] = incl - a0 - a1;
+            s_prefix[2 * t + 1] = incl - a1;
+        }
+        if (t == 511) s_prefix[kChunkSmem] = incl;
+    }
     wait_peers(c, ch, 0, e, peer_off);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-    for (int k = 0; k < nchunks; ++k) {
-        const ChunkDesc d = chunks[k];
-        const int64_t nvec = d.bytes >> 4;
-        const uint4* s = reinterpret_cast<const uint4*>(c.data[d.peer] + peer_off[d.peer] + d.src_off);
-        uint4* o = reinterpret_cast<uint4*>(dst + d.dst_off);
-        int64_t i = tid;
-        for (; i + 7 * nthr < nvec; i += 8 * nthr) {
-            uint4 r[8];
+    if (flat) {
+        // every thread keeps 8 independent 16-byte peer loads in flight regardless of how small the chunks are (an EP
+        // exchange is E/EP x EP blocks of a few hundred KB: swept one by one they never fill the unrolled loop)
+        const int64_t vtot = s_prefix[nchunks < kChunkSmem ? nchunks : kChunkSmem];
+        constexpr int UN = 8;
+        for (int64_t v0 = tid; v0 < vtot; v0 += nthr * UN) {
+            uint4 r[UN];
+            uint4* d[UN];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) r[u] = ldg_v4(s + i + u * nthr);
+            for (int u = 0; u < UN; ++u) {
+                const int64_t v = v0 + (int64_t)u * nthr;
+                d[u] = nullptr;
+                if (v < vtot) {
+                    const int k = find_segment(s_prefix, nchunks, v);
+                    const ChunkDesc cd = chunks[k];
+                    const int64_t o = (v - s_prefix[k]) << 4;
+                    r[u] = ldg_v4(c.data[cd.peer] + peer_off[cd.peer] + cd.src_off + o);
+                    d[u] = reinterpret_cast<uint4*>(dst + cd.dst_off + o);
+                }
+            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) o[i + u * nthr] = r[u];
+            for (int u = 0; u < UN; ++u)
+                if (d[u]) stg_v4(d[u], r[u]);
         }
-        for (; i < nvec; i += nthr) o[i] = ldg_v4(s + i);
+    } else {
+        for (int k = 0; k < nchunks; ++k) {
+            const ChunkDesc d = chunks[k];
+            const int64_t nvec = d.bytes >> 4;
+            const uint4* s = reinterpret_cast<const uint4*>(c.data[d.peer] + peer_off[d.peer] + d.src_off);
+            uint4* o = reinterpret_cast<uint4*>(dst + d.dst_off);
+            int64_t i = tid;
+            for (; i + 7 * nthr < nvec; i += 8 * nthr) {
+                uint4 r[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] = ldg_v4(s + i + u * nthr);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) o[i + u * nthr] = r[u];
+            }
+            for (; i < nvec; i += nthr) o[i] = ldg_v4(s + i);
+        }
     }
     if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
+}
+
+// ---- FSDP2 unit all-gather with the copy-out fused in ----------------------------------------------------------
+// Replaces DefaultAllGather (torch/_fsdp_collectives.py:81-95) *and* foreach_all_gather_copy_out's
+// fsdp::split_with_sizes_copy (:196-212, :346-412): every rank's shard row (the concatenation of its shards of the
+// unit's parameters, written by the copy-in) is pulled from its owner and stored straight into the per-parameter
+// unsharded tensors, rank p's piece of parameter i at dst_i + p * bytes_i. The [world, row] all-gather output buffer
+// is never filled and the extra read + write pass over the whole unit disappears.
+constexpr int kScatterMax = 64;
+struct ScatterArgs {
+    int n;
+    int vec_ok;                          // every offset / size / destination is a multiple of 16 bytes
+    int64_t off[kScatterMax];            // byte offset of parameter i inside a shard row
+    int64_t bytes[kScatterMax];          // bytes of one rank's shard of parameter i
+    uint8_t* dst[kScatterMax];           // the parameter's unsharded tensor (local memory, world * bytes)
+};
+
+__global__ void __launch_bounds__(512)
+allgather_scatter_kernel(CommDev c, int ch, int64_t off, int64_t shard_bytes, ScatterArgs a) {
+    __shared__ int64_t peer_off[kMaxWorld];
+    __shared__ int64_t s_prefix[kScatterMax + 1];  // 16-byte vectors before parameter i inside a row
+    __shared__ int64_t s_off[kScatterMax], s_bytes[kScatterMax];
+    __shared__ uint8_t* s_dst[kScatterMax];
+    const uint32_t e = c.state[ch] + 1;
+    if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
+    if (threadIdx.x == 0) {
+        int64_t acc = 0;
+        for (int i = 0; i < a.n; ++i) {
+            s_prefix[i] = acc;
+            acc += a.bytes[i] >> 4;
+        }
+        s_prefix[a.n] = acc;
+    }
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
+        s_off[i] = a.off[i];
+        s_bytes[i] = a.bytes[i];
+        s_dst[i] = a.dst[i];
+    }
+    wait_peers(c, ch, 0, e, peer_off);  // ends with a block-wide barrier
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    for (int q = 0; q < c.world; ++q) {
+        const int p = (c.rank + q) % c.world;  // q = 0: this rank's own shard; sources staggered over the peers
+        const uint8_t* src = c.data[p] + peer_off[p] + (int64_t)p * shard_bytes;
+        if (a.vec_ok) {
+            const int64_t vrow = s_prefix[a.n];
+            constexpr int UN = 8;  // independent 16-byte peer loads in flight per thread
+            for (int64_t v0 = tid; v0 < vrow; v0 += nthr * UN) {
+                uint4 r[UN];
+                uint4* d[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int64_t v = v0 + (int64_t)u * nthr;
+                    d[u] = nullptr;
+                    if (v < vrow) {
+                        const int i = find_segment(s_prefix, a.n, v);
+                        const int64_t k = (v - s_prefix[i]) << 4;
+                        r[u] = ldg_v4(src + s_off[i] + k);
+                        d[u] = reinterpret_cast<uint4*>(s_dst[i] + (int64_t)p * s_bytes[i] + k);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u)
+                    if (d[u]) stg_v4(d[u], r[u]);
+            }
+        } else {
+            for (int i = 0; i < a.n; ++i) grid_copy(s_dst[i] + (int64_t)p * s_bytes[i], src + s_off[i], s_bytes[i]);
+        }
+    }
+    if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
+}
+
+// ---- FSDP2 unit reduce-scatter with the copy-in fused in -----------------------------------------------------------
+// Replaces foreach_reduce_scatter_copy_in (torch._chunk_cat, _fsdp_collectives.py:667-675) + DefaultReduceScatter
+// (:116-131) + the divide (:701-759). Phase A reads the unit's bf16 gradients *in place* through a pointer table and
+// pushes chunk p of every parameter (dim-0 zero-padded to a multiple of world, as chunk_cat lays it out) to peer p's
+// staging buffer, slot = this rank, with 16-byte NVLink stores (posted writes: no round-trip latency to cover, so few
+// CTAs keep the links busy). Phase B, after every peer's "pushed" flag has arrived, sums the world slots of the local
+// staging buffer in rank order 0..N-1 in fp32 (deterministic, bit-identical to the fp32 reduce-scatter of the same
+// gradients because bf16 -> fp32 is exact), scales, and writes the fp32 shard.
+constexpr int kPushMax = 64;
+struct PushArgs {
+    int n;
+    int world;
+    int vec_ok;    // chunks are multiples of 8 elements and gradient pointers are 16-byte aligned
+    int64_t row;   // elements per rank row = sum of chunks
+    const __nv_bfloat16* src[kPushMax];
+    int64_t numel[kPushMax];
+    int64_t chunk[kPushMax];  // off[i] = sum of chunk[0..i)
+};
+
+__device__ __forceinline__ uint4 ldg_cg_v4(const void* p) {  // L2-coherent load (data written by peers over NVLink)
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+template <int W>
+__global__ void __launch_bounds__(512)
+reduce_scatter_push_bf16_kernel(CommDev c, int ch, int64_t off, PushArgs a, float scale, float* __restrict__ out) {
+    __shared__ int64_t peer_off[kMaxWorld];
+    __shared__ int64_t s_prefix[kPushMax + 1];  // element offset of parameter i inside a row
+    __shared__ const __nv_bfloat16* s_src[kPushMax];
+    __shared__ int64_t s_numel[kPushMax], s_chunk[kPushMax];
+    __shared__ int s_last;
+    const uint32_t e = c.state[ch] + 1;
+    if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);  // "my staging buffer (at off) is free for epoch e"
+    if (threadIdx.x == 0) {
+        int64_t acc = 0;
+        for (int i = 0; i < a.n; ++i) {
+            s_prefix[i] = acc;
+            acc += a.chunk[i];
+        }
+        s_prefix[a.n] = acc;
+    }
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
+        s_src[i] = a.src[i];
+        s_numel[i] = a.numel[i];
+        s_chunk[i] = a.chunk[i];
+    }
+    wait_peers(c, ch, 0, e, peer_off);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const int64_t row = a.row;
+    // ---- phase A: push -------------------------------------------------------------------------------------------
+    for (int q = 0; q < c.world; ++q) {
+        const int p = (c.rank + q) % c.world;  // q = 0: own chunk into the local staging slot
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.data[p] + peer_off[p]) + (int64_t)c.rank * row;
+        if (a.vec_ok) {
+            const int64_t nvec = row >> 3;
+            constexpr int UN = 4;
+            for (int64_t v0 = tid; v0 < nvec; v0 += nthr * UN) {
+                uint4 r[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int64_t v = v0 + (int64_t)u * nthr;
+                    if (v < nvec) {
+                        const int64_t x = v << 3;
+                        const int i = find_segment(s_prefix, a.n, x);
+                        const int64_t g = (int64_t)p * s_chunk[i] + (x - s_prefix[i]);  // element of gradient i
+                        if (g + 8 <= s_numel[i]) {
+                            r[u] = ldg_stream(s_src[i] + g);
+                        } else {  // dim-0 padding: zeros
+                            __align__(16) __nv_bfloat16 t[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) t[j] = g + j < s_numel[i] ? s_src[i][g + j] : __float2bfloat16_rn(0.f);
+                            r[u] = *reinterpret_cast<uint4*>(t);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int64_t v = v0 + (int64_t)u * nthr;
+                    if (v < nvec) stg_v4(dst + (v << 3), r[u]);
+                }
+            }
+        } else {
+            for (int64_t x = tid; x < row; x += nthr) {
+                const int i = find_segment(s_prefix, a.n, x);
+                const int64_t g = (int64_t)p * s_chunk[i] + (x - s_prefix[i]);
+                dst[x] = g < s_numel[i] ? s_src[i][g] : __float2bfloat16_rn(0.f);
+            }
+        }
+    }
+    // every store of this CTA is performed system-wide before the CTA counts itself as done
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(c.state + kMaxChannels + ch, 1u);
+        s_last = (prev == gridDim.x - 1);
+        __threadfence();
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        signal_peers(c, ch, 1, e);  // "everything I owe you for epoch e has been written"
+    }
+    wait_peers(c, ch, 1, e);
+    // ---- phase B: reduce the world slots of the local staging buffer in rank order -------------------------------
+    const __nv_bfloat16* stage = reinterpret_cast<const __nv_bfloat16*>(c.data[c.rank] + off);
+    constexpr int NP = W ? W : kMaxWorld;
+    constexpr int UN2 = W == 0 ? 2 : (W <= 2 ? 8 : 4);
+    if (a.vec_ok && ((((uintptr_t)out) & 15) == 0)) {
+        const int64_t nvec = row >> 3;
+        for (int64_t v0 = tid; v0 < nvec; v0 += nthr * UN2) {
+            uint4 r[UN2][NP];
+#pragma unroll
+            for (int u = 0; u < UN2; ++u) {
+                const int64_t v = v0 + (int64_t)u * nthr;
+#pragma unroll
+                for (int s = 0; s < NP; ++s)
+                    if (s < c.world && v < nvec) r[u][s] = ldg_cg_v4(stage + (int64_t)s * row + (v << 3));
+            }
+#pragma unroll
+            for (int u = 0; u < UN2; ++u) {
+                const int64_t v = v0 + (int64_t)u * nthr;
+                if (v < nvec) {
+                    float acc[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+                    for (int s = 0; s < NP; ++s)
+                        if (s < c.world) {
+                            const uint32_t w[4] = {r[u][s].x, r[u][s].y, r[u][s].z, r[u][s].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                acc[2 * j] += __uint_as_float(w[j] << 16);
+                                acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                            }
+                        }
+                    float* o = out + (v << 3);
+                    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(acc[0] * scale), "f"(acc[1] * scale), "f"(acc[2] * scale), "f"(acc[3] * scale) : "memory");
+                    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + 4), "f"(acc[4] * scale), "f"(acc[5] * scale), "f"(acc[6] * scale), "f"(acc[7] * scale) : "memory");
+                }
+            }
+        }
+    } else {
+        for (int64_t x = tid; x < row; x += nthr) {
+            float acc = 0.f;
+            for (int s = 0; s < c.world; ++s) {
+                uint16_t v;
+                asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(stage + (int64_t)s * row + x) : "memory");
+                acc += __uint_as_float((uint32_t)v << 16);
+            }
+            out[x] = acc * scale;
+        }
+    }
+    // completion: no peer handshake is needed (peers write this staging buffer again only after the READY flag of this
+    // rank's *next* reduce-scatter kernel, which is stream-ordered after this one); the last CTA resets the counters
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(c.state + kStateCounter2 + ch, 1u);
+        if (prev == gridDim.x - 1) {
+            c.state[kMaxChannels + ch] = 0;
+            c.state[kStateCounter2 + ch] = 0;
+            __threadfence();
+            c.state[ch] = e;
+        }
+    }
 }
 
 }  // namespace vb
@@ -521,7 +827,7 @@ extern "C" int vb200_comm_create(void** comm, int32_t rank, int32_t world, void*
         h->dev.sig[p] = (uint64_t*)(p < world ? peer_signal[p] : peer_signal[rank]);
     }
     h->data_bytes = data_bytes;
-    const size_t state_bytes = sizeof(uint32_t) * (2 * kMaxChannels + 4);
+    const size_t state_bytes = sizeof(uint32_t) * kStateWords;
     cudaError_t e = cudaMalloc((void**)&h->dev.state, state_bytes);
     if (e == cudaSuccess) e = cudaMemset(h->dev.state, 0, state_bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -543,7 +849,7 @@ extern "C" int vb200_comm_destroy(void* comm) {
 extern "C" int vb200_comm_check(void* comm) {
     CommHost* h = (CommHost*)comm;
     uint32_t err = 0;
-    VB_CUDA_TRY(cudaMemcpy(&err, h->dev.state + 2 * kMaxChannels, 4, cudaMemcpyDeviceToHost));
+    VB_CUDA_TRY(cudaMemcpy(&err, h->dev.state + kStateError, 4, cudaMemcpyDeviceToHost));
     if (err) return vb200_set_error(VB200_ETIMEOUT, "a peer signal wait timed out");
     return VB200_OK;
 }
@@ -658,6 +964,74 @@ extern "C" int vb200_fsdp_pack_bf16(const int64_t* desc, int32_t n, int32_t worl
         vb200_count_launch(1);
         VB_HOST_CHECK_LAUNCH();
     }
+    return VB200_OK;
+}
+
+
+// table: n x 3 int64 = {byte offset of the parameter inside a shard row, bytes of one rank's shard, destination pointer}
+extern "C" int vb200_allgather_scatter(void* comm, int32_t channel, int64_t region_offset, int64_t shard_bytes,
+                                       const int64_t* table, int32_t n, int32_t num_ctas, void* stream) {
+    if (check_ch(channel)) return VB200_EINVAL;
+    CommHost* h = (CommHost*)comm;
+    if (region_offset < 0 || (region_offset & 255) || shard_bytes < 0 || (shard_bytes & 1) || n < 0 || (n > 0 && !table) ||
+        region_offset + shard_bytes * h->dev.world > h->data_bytes)
+        return vb200_set_error(VB200_EINVAL, "allgather_scatter: offset must be 256-byte aligned and inside the region");
+    if (n > kScatterMax) return vb200_set_error(VB200_EINVAL, "allgather_scatter: at most 64 parameters per call");
+    ScatterArgs a;
+    a.n = n;
+    a.vec_ok = (shard_bytes & 15) == 0;
+    for (int i = 0; i < n; ++i) {
+        a.off[i] = table[3 * i];
+        a.bytes[i] = table[3 * i + 1];
+        a.dst[i] = (uint8_t*)(uintptr_t)table[3 * i + 2];
+        if (a.off[i] < 0 || a.bytes[i] < 0 || (a.bytes[i] & 1) || a.off[i] + a.bytes[i] > shard_bytes || (a.bytes[i] > 0 && !a.dst[i]))
+            return vb200_set_error(VB200_EINVAL, "allgather_scatter: inconsistent parameter table");
+        if ((a.off[i] | a.bytes[i] | (int64_t)(uintptr_t)a.dst[i]) & 15) a.vec_ok = 0;
+    }
+    allgather_scatter_kernel<<<clamp_ctas(num_ctas), 512, 0, (cudaStream_t)stream>>>(h->dev, channel, region_offset, shard_bytes, a);
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+// desc: n x 3 int64 = {gradient pointer (bf16, contiguous), numel, chunk elements}; the staging buffer
+// [world, row_elems] bf16 sits at region_offset of every rank's region; out: row_elems fp32
+extern "C" int vb200_reduce_scatter_push_bf16(void* comm, int32_t channel, int64_t region_offset, const int64_t* desc,
+                                              int32_t n, int64_t row_elems, float scale, float* out, int32_t num_ctas,
+                                              void* stream) {
+    if (check_ch(channel)) return VB200_EINVAL;
+    CommHost* h = (CommHost*)comm;
+    if (region_offset < 0 || (region_offset & 255) || row_elems < 0 || n < 0 || (n > 0 && (!desc || !out)) ||
+        region_offset + row_elems * 2 * h->dev.world > h->data_bytes)
+        return vb200_set_error(VB200_EINVAL, "reduce_scatter_push: staging must be 256-byte aligned and inside the region");
+    if (n > kPushMax) return vb200_set_error(VB200_EINVAL, "reduce_scatter_push: at most 64 parameters per call");
+    PushArgs a;
+    a.n = n;
+    a.world = h->dev.world;
+    a.row = row_elems;
+    a.vec_ok = 1;
+    int64_t acc = 0;
+    for (int i = 0; i < n; ++i) {
+        a.src[i] = (const __nv_bfloat16*)(uintptr_t)desc[3 * i];
+        a.numel[i] = desc[3 * i + 1];
+        a.chunk[i] = desc[3 * i + 2];
+        if (a.numel[i] < 0 || a.chunk[i] < 0 || a.numel[i] > a.chunk[i] * h->dev.world || (a.numel[i] > 0 && !a.src[i]))
+            return vb200_set_error(VB200_EINVAL, "reduce_scatter_push: inconsistent descriptor");
+        if ((a.chunk[i] & 7) || ((uintptr_t)a.src[i] & 15)) a.vec_ok = 0;
+        acc += a.chunk[i];
+    }
+    if (acc != row_elems) return vb200_set_error(VB200_EINVAL, "reduce_scatter_push: chunks do not add up to the row");
+    const int g = clamp_ctas(num_ctas);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* gen = getenv("VB200_RS_GENERIC");
+    switch ((gen && gen[0] == '1') ? 0 : h->dev.world) {
+        case 1: reduce_scatter_push_bf16_kernel<1><<<g, 512, 0, st>>>(h->dev, channel, region_offset, a, scale, out); break;
+        case 2: reduce_scatter_push_bf16_kernel<2><<<g, 512, 0, st>>>(h->dev, channel, region_offset, a, scale, out); break;
+        case 4: reduce_scatter_push_bf16_kernel<4><<<g, 512, 0, st>>>(h->dev, channel, region_offset, a, scale, out); break;
+        default: reduce_scatter_push_bf16_kernel<0><<<g, 512, 0, st>>>(h->dev, channel, region_offset, a, scale, out); break;
+    }
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
 }
 

@@ -28,7 +28,7 @@ from dataclasses import dataclass
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, prof
 from . import functional as F
 from ._lib import VB200Error, check, stream_ptr
 from .moe import _gather_raw, group_gemm_same_mn, group_gemm_same_nk, moe_route
@@ -49,15 +49,23 @@ class EPContext:
         self.ep_size = self.symm.world
         self.rank = self.symm.rank
         self.num_ctas = num_ctas
-        self._bufs: dict[tuple[str, int], torch.Tensor] = {}
+        self._bufs: dict[str, torch.Tensor] = {}
 
     def staging(self, tag: str, nbytes: int) -> torch.Tensor:
-        """Persistent symmetric buffer per (tag, size): reuse is ordered by the collectives' own barriers."""
-        nbytes = (nbytes + 255) // 256 * 256
-        key = (tag, nbytes)
-        if key not in self._bufs:
-            self._bufs[key] = self.symm.empty((nbytes,), torch.uint8, arena="misc")
-        return self._bufs[key]
+        """ONE persistent symmetric buffer per tag, grown geometrically: receive sizes depend on the routing and differ on
+        nearly every layer and step, so a buffer per (tag, size) would leak the arena. A larger buffer replaces the old one
+        (whose block returns to the arena; every user runs on the caller's stream and the pull kernels only retire after
+        all peers finished reading, so stream order makes the reuse safe). Each collective publishes the offset of the
+        buffer it exposes, so ranks growing at different times is fine."""
+        nbytes = (max(int(nbytes), 1) + 255) // 256 * 256
+        cur = self._bufs.get(tag)
+        if cur is None or cur.numel() < nbytes:
+            want = nbytes if cur is None else max(nbytes, cur.numel() * 3 // 2)
+            want = (want + 255) // 256 * 256
+            self._bufs.pop(tag, None)
+            del cur
+            self._bufs[tag] = self.symm.empty((want,), torch.uint8, arena="misc")
+        return self._bufs[tag]
 
 
 @dataclass
@@ -103,41 +111,46 @@ def make_plan(ctx: EPContext, selected_experts: torch.Tensor, num_experts: int, 
     cbuf[r * num_experts : (r + 1) * num_experts].copy_(splits)
     ctx.symm.all_gather_inplace(cbuf, num_experts, CH_EP_COUNTS, 1)
     counts = cbuf.view(ep, num_experts).to("cpu", non_blocking=False).to(torch.int64)  # the one host sync
-    row = hidden * 2
-    excl = torch.cumsum(counts, dim=1) - counts  # [EP, E]: offset of expert e inside rank s's send order
-    input_splits = counts[r].view(ep, el).sum(dim=1).tolist()
-    mine = counts[:, r * el : (r + 1) * el]  # [EP, El]
-    output_splits = mine.sum(dim=1).tolist()
-    fwd, dst = [], 0
-    for le in range(el):
-        e = r * el + le
-        for s in range(ep):
-            n = int(counts[s, e])
-            if n:
-                fwd.append((s, int(excl[s, e]) * row, dst * row, n * row))
-            dst += n
-    total_recv = dst
-    cumsum_local = torch.cumsum(mine.sum(dim=0), dim=0).to(torch.int32).to(dev, non_blocking=True)
-    # return path: for every expert e (owner p), my block sits in p's output at
-    #   rows(sum_{le'<le} sum_s C[s, p*el+le']) + sum_{s<r} C[s, e]
-    bwd = []
-    per_expert_total = counts.sum(dim=0)  # [E]
-    for p in range(ep):
-        base = 0
-        for le in range(el):
-            e = p * el + le
-            n = int(counts[r, e])
-            if n:
-                src_row = base + int(counts[:r, e].sum())
-                bwd.append((p, src_row * row, int(excl[r, e]) * row, n * row))
-            base += int(per_expert_total[e])
+    input_splits, output_splits, total_recv, cumsum_host, fwd, bwd = plan_chunks(counts, r, hidden * 2)
+    cumsum_local = cumsum_host.to(torch.int32).to(dev, non_blocking=True)
     return EPPlan(ctx, T, K, hidden, sidx, counts, input_splits, output_splits, total_recv, cumsum_local,
-                  _chunk_tensor(fwd, dev), len(fwd), _chunk_tensor(bwd, dev), len(bwd))
+                  fwd.to(dev, non_blocking=True), fwd.shape[0], bwd.to(dev, non_blocking=True), bwd.shape[0])
+
+
+def plan_chunks(counts: torch.Tensor, r: int, row: int):
+    """Host geometry of one EP exchange from the gathered counts matrix ``counts[s, e]`` (int64, CPU) = rows rank ``s``
+    sends to expert ``e``; ``row`` = bytes per token row. Vectorised (no per-expert Python loops: Qwen3-30B-A3B calls this
+    48 x 3 times per step). Returns (input_splits, output_splits, total_recv, inclusive cumsum of rows per local expert,
+    forward chunk list, return chunk list); chunk lists are int64 ``[n, 4]`` = {src_off, dst_off, bytes, peer} as the C
+    struct ``ChunkDesc`` (csrc/p2p.cu), zero-sized blocks included (the kernel skips them), in
+    expert-major / source-minor order — the order ``sort_chunks_by_idxs`` gives the reference (moe_utils.py:81-99)."""
+    ep, E = counts.shape
+    el = E // ep
+    excl = torch.cumsum(counts, dim=1) - counts  # [EP, E]: row offset of expert e inside rank s's send order
+    input_splits = counts[r].view(ep, el).sum(dim=1).tolist()
+    mine = counts[:, r * el : (r + 1) * el]  # [EP, El]: what every source sends to my experts
+    output_splits = mine.sum(dim=1).tolist()
+    # forward: my receive buffer is ordered (local expert, source); block (le, s) comes from rank s at excl[s, e]
+    n_fwd = mine.t().contiguous().view(-1)  # [El * EP] rows of block (le, s)
+    dst_fwd = torch.cumsum(n_fwd, 0) - n_fwd
+    total_recv = int(n_fwd.sum())
+    src_fwd = excl[:, r * el : (r + 1) * el].t().contiguous().view(-1)
+    peer_fwd = torch.arange(ep, dtype=torch.int64).repeat(el)
+    fwd = torch.stack([src_fwd * row, dst_fwd * row, n_fwd * row, peer_fwd], dim=1)
+    cumsum_host = torch.cumsum(mine.sum(dim=0), dim=0)
+    # return path: for expert e = p*el + le (owner p) my block sits in p's buffer at
+    #   rows(sum_{le' < le} sum_s C[s, p*el + le']) + sum_{s < r} C[s, e]   and goes back to row excl[r, e] of mine
+    per_expert = counts.sum(dim=0).view(ep, el)  # [p, le]
+    base = (torch.cumsum(per_expert, dim=1) - per_expert).view(-1)  # rows before expert e inside its owner's buffer
+    before_me = counts[:r].sum(dim=0)  # [E]
+    bwd = torch.stack([(base + before_me) * row, excl[r] * row, counts[r] * row,
+                       torch.arange(ep, dtype=torch.int64).repeat_interleave(el)], dim=1)
+    return input_splits, output_splits, total_recv, cumsum_host, fwd.contiguous(), bwd.contiguous()
 
 
 def _pull(ctx: EPContext, channel: int, src_buf: torch.Tensor, chunks: torch.Tensor, n: int, out: torch.Tensor) -> None:
     lib = _lib.load()
-    with torch.cuda.device(out.device):
+    with torch.cuda.device(out.device), prof.span("ep_pull", out.numel() * out.element_size() * (ctx.ep_size - 1) / ctx.ep_size):
         check(lib.vb200_chunk_pull(ctx.symm.comm, channel, ctx.symm.offset_of(src_buf), chunks.data_ptr(), n,
                                    out.data_ptr(), ctx.num_ctas, stream_ptr()), "vb200_chunk_pull")
 

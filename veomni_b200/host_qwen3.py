@@ -103,12 +103,13 @@ class Qwen3Attention(nn.Module):
         self.q_norm = Qwen3RMSNorm(D, cfg.rms_norm_eps)
         self.k_norm = Qwen3RMSNorm(D, cfg.rms_norm_eps)
         self.scaling = D**-0.5
-        # gradient checkpointing: (forward id, o, lse) of the first forward, consumed by the recompute
+        # gradient checkpointing: {forward id: (o, lse)} of first forwards, each consumed by its own recompute. The id
+        # travels through the checkpointed call's arguments, so a recompute can only ever pick up the (o, lse) of the
+        # forward it re-runs (two forwards before the first backward included).
         self.keep_attention = False
-        self._fwd_id = 0
-        self._stash = None
+        self._stash: dict = {}
 
-    def forward(self, x, cos, sin, cu_seqlens, max_seqlen, sp_group=None):
+    def forward(self, x, cos, sin, cu_seqlens, max_seqlen, sp_group=None, fwd_id=None):
         # x: [T_local, hidden]; cos/sin: [T_local, D]
         cfg = self.cfg
         T, D = x.shape[0], cfg.head_dim
@@ -129,14 +130,15 @@ class Qwen3Attention(nn.Module):
                 k = torch.repeat_interleave(k, P // cfg.num_key_value_heads, dim=1)
                 v = torch.repeat_interleave(v, P // cfg.num_key_value_heads, dim=1)
             q, k, v = U.gather_seq_scatter_heads_qkv(q, k, v, seq_dim=0, head_dim=1, group=sp_group)
-        st = self._stash
-        if self.keep_attention and torch.is_grad_enabled() and st is not None and st[0] == self._fwd_id:
-            self._stash = None  # recompute pass: reuse the deterministic result instead of relaunching
-            o = flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen, self.scaling, True, replay=(st[1], st[2]))
+        keep = self.keep_attention and fwd_id is not None and torch.is_grad_enabled()
+        st = self._stash.pop(fwd_id, None) if keep else None
+        if st is not None and st[0].shape == (q.shape[0], q.shape[1], q.shape[2]) and st[1].shape[-1] == q.shape[0]:
+            # recompute pass of this very forward: reuse the (deterministic) result instead of relaunching the kernel
+            o = flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen, self.scaling, True, replay=st)
         else:
             o, lse = flash_attn_varlen(q, k, v, cu_seqlens, max_seqlen, self.scaling, True, return_lse=True)
-            if self.keep_attention and self.training and torch.is_grad_enabled():
-                self._stash = (self._fwd_id, o.detach(), lse)
+            if keep and self.training:
+                self._stash[fwd_id] = (o.detach(), lse)
         if sp_group is not None:
             o = U.gather_heads_scatter_seq(o, head_dim=1, seq_dim=0, group=sp_group)
         return self.o_proj(o.reshape(T, -1))
@@ -149,11 +151,11 @@ class Qwen3DecoderLayer(nn.Module):
         self.mlp = Qwen3MLP(cfg)
         self.input_layernorm = Qwen3RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
         self.post_attention_layernorm = Qwen3RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
-        self.fuse_add_norm = os.environ.get("VB200_FUSE_ADD_NORM", "0") == "1"
+        self.fuse_add_norm = os.environ.get("VB200_FUSE_ADD_NORM", "1") == "1"
 
-    def forward(self, h, cos, sin, cu_seqlens, max_seqlen, sp_group=None):
-        a = self.self_attn(self.input_layernorm(h), cos, sin, cu_seqlens, max_seqlen, sp_group)
-        if self.fuse_add_norm:  # experimental: residual add fused into the post-attention RMSNorm
+    def forward(self, h, cos, sin, cu_seqlens, max_seqlen, sp_group=None, fwd_id=None):
+        a = self.self_attn(self.input_layernorm(h), cos, sin, cu_seqlens, max_seqlen, sp_group, fwd_id)
+        if self.fuse_add_norm:  # residual add fused into the post-attention RMSNorm
             n = self.post_attention_layernorm
             x, h = F.fused_add_rms_norm(a, h, n.weight, n.variance_epsilon)
             return h + self.mlp(x)
@@ -192,13 +194,17 @@ class Qwen3ForCausalLM(nn.Module):
 
     @torch.no_grad()
     def init_weights(self, seed: int = 0):
-        """HF ``_init_weights`` semantics: N(0, initializer_range) for Linear/Embedding, ones for norms."""
-        g = torch.Generator(device=self.lm_head.weight.device).manual_seed(seed)
+        """HF ``_init_weights`` semantics: N(0, initializer_range) for Linear/Embedding, ones for norms. Works on plain
+        tensors and on FSDP2 DTensor shards (each rank fills its local shard; meta-init path of build_parallelize_model)."""
+        dev = self.lm_head.weight.device
+        g = torch.Generator(device=dev).manual_seed(seed + (_rank_seed() if _is_dtensor(self.lm_head.weight) else 0))
         for m in self.modules():
             if isinstance(m, (nn.Linear, nn.Embedding)):
-                m.weight.normal_(0.0, self.config.initializer_range, generator=g)
+                _local(m.weight).normal_(0.0, self.config.initializer_range, generator=g)
             elif isinstance(m, Qwen3RMSNorm):
-                m.weight.fill_(1.0)
+                _local(m.weight).fill_(1.0)
+        cfg = self.config
+        self.inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64, device=dev).float() / cfg.head_dim))
 
     def rotary(self, position_ids: torch.Tensor, dtype: torch.dtype):
         """Qwen3RotaryEmbedding.forward (:181-192): fp32 angles, cos/sin cast to the activation dtype."""
@@ -217,11 +223,14 @@ class Qwen3ForCausalLM(nn.Module):
         cos, sin = self.rotary(position_ids, h.dtype)
         self._fwd_counter += 1
         ckpt = self.gradient_checkpointing and self.training
+        fid = self._fwd_counter
         for layer in self.model.layers:
-            layer.self_attn.keep_attention = ckpt and self.keep_attention_in_checkpoint
-            layer.self_attn._fwd_id = self._fwd_counter
+            att = layer.self_attn
+            att.keep_attention = ckpt and self.keep_attention_in_checkpoint
+            for old in [k for k in att._stash if k < fid - 4]:  # forwards that never got a backward (bounded memory)
+                del att._stash[old]
             if ckpt:
-                h = checkpoint(layer, h, cos, sin, cu_seqlens, max_seqlen, self.sp_group, use_reentrant=False)
+                h = checkpoint(layer, h, cos, sin, cu_seqlens, max_seqlen, self.sp_group, fid, use_reentrant=False)
             else:
                 h = layer(h, cos, sin, cu_seqlens, max_seqlen, self.sp_group)
         h = self.model.norm(h)
@@ -239,6 +248,22 @@ class Qwen3ForCausalLM(nn.Module):
             loss, _ = b200_cross_entropy(self.lm_head(h).float().view(-1, self.config.vocab_size), shift_labels,
                                          self.config.vocab_size)
         return loss
+
+
+def _is_dtensor(t) -> bool:
+    from torch.distributed._tensor import DTensor
+
+    return isinstance(t, DTensor)
+
+
+def _local(t):
+    return t.to_local() if _is_dtensor(t) else t
+
+
+def _rank_seed() -> int:
+    import torch.distributed as dist
+
+    return 7919 * (dist.get_rank() + 1) if dist.is_initialized() else 0
 
 
 def flops_per_token(cfg: Qwen3Config, seq_lens: list[int]) -> float:

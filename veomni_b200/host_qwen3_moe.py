@@ -79,8 +79,8 @@ class Qwen3MoeDecoderLayer(nn.Module):
         self.input_layernorm = Qwen3RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
         self.post_attention_layernorm = Qwen3RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
 
-    def forward(self, h, cos, sin, cu_seqlens, max_seqlen, sp_group=None):
-        h = h + self.self_attn(self.input_layernorm(h), cos, sin, cu_seqlens, max_seqlen, sp_group)
+    def forward(self, h, cos, sin, cu_seqlens, max_seqlen, sp_group=None, fwd_id=None):
+        h = h + self.self_attn(self.input_layernorm(h), cos, sin, cu_seqlens, max_seqlen, sp_group, fwd_id)
         return h + self.mlp(self.post_attention_layernorm(h))
 
 
@@ -93,14 +93,17 @@ class Qwen3MoeForCausalLM(Qwen3ForCausalLM):
 
     @torch.no_grad()
     def init_weights(self, seed: int = 0):
+        from .host_qwen3 import _is_dtensor, _local, _rank_seed
+
         super().init_weights(seed)
-        g = torch.Generator(device=self.lm_head.weight.device).manual_seed(seed + 1)
+        sharded = _is_dtensor(self.lm_head.weight)
+        g = torch.Generator(device=self.lm_head.weight.device).manual_seed(seed + 1 + (_rank_seed() if sharded else 0))
         for m in self.modules():
             if isinstance(m, Qwen3MoeExperts):
-                m.gate_up_proj.normal_(0.0, self.config.initializer_range, generator=g)
-                m.down_proj.normal_(0.0, self.config.initializer_range, generator=g)
+                _local(m.gate_up_proj).normal_(0.0, self.config.initializer_range, generator=g)
+                _local(m.down_proj).normal_(0.0, self.config.initializer_range, generator=g)
             elif isinstance(m, Qwen3MoeTopKRouter):
-                m.weight.normal_(0.0, self.config.initializer_range, generator=g)
+                _local(m.weight).normal_(0.0, self.config.initializer_range, generator=g)
 
     def get_parallel_plan(self):
         from .parallel_plan import qwen3_moe_parallel_plan

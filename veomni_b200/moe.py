@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, prof
 from . import functional as F
 from ._lib import VB200Error, check, stream_ptr
 
@@ -116,7 +116,8 @@ def _cumsum32(c: torch.Tensor) -> torch.Tensor:
 
 def _gg(mode: int, a, b, c, cumsum, G, rows, m, n, k):
     lib = _lib.load()
-    with torch.cuda.device(a.device):
+    flops = 2.0 * rows * (m * n if mode == 2 else n * k)
+    with torch.cuda.device(a.device), prof.span("group_gemm", flops):
         check(lib.vb200_group_gemm(mode, a.data_ptr(), b.data_ptr(), c.data_ptr(), cumsum.data_ptr(), G, rows, m, n, k,
                                    stream_ptr()), "vb200_group_gemm")
     return c

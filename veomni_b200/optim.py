@@ -1,14 +1,23 @@
-"""AdamW on the multi-tensor kernel (EXPERIMENTAL: written in round 1, not yet validated on hardware — nothing in the
-default path uses it; ``bench.py --b200-adamw`` and the gated test in tests/test_ops_gpu.py exercise it).
+"""AdamW on the multi-tensor kernel (``vb200_multi_adamw``).
 
 The reference builds ``torch.optim.AdamW(..., fused=True)`` over the fp32 DTensor shards
-(veomni/optim/optimizer.py:261-328; SURVEY.md §8(f)4 lists the optimizer step as "next"). PyTorch's fused kernel moves
-the 28 bytes per parameter at ~4.5 TB/s on the ~400 shards of Qwen3-8B (51 ms of the 339 ms single-GPU step); this
-class runs the same arithmetic as one launch over a device table of (param, grad, exp_avg, exp_avg_sq) entries, and can
-fold a gradient-clip coefficient in (``grad_scale``) instead of a separate scaling pass.
+(veomni/optim/optimizer.py:261-328). PyTorch's fused kernel moves the 28 bytes per parameter at
+~4.5 TB/s on the ~400 shards of Qwen3-8B (51 ms of a 339 ms single-GPU step); this class runs the same arithmetic as ONE
+launch over a device table of (param, grad, exp_avg, exp_avg_sq) entries and can fold the gradient-clip coefficient in
+(``step(grad_scale=...)``) instead of a separate scaling pass over the gradients.
 
-Same hyper-parameters, same state keys (``step``, ``exp_avg``, ``exp_avg_sq``) as ``torch.optim.AdamW``; no amsgrad,
-maximize, capturable or differentiable modes; fp32 CUDA parameters only (anything else raises).
+Two layouts:
+
+* default — fp32 parameters (plain tensors or FSDP2 DTensor shards) with fp32 or bf16 gradients: same
+  hyper-parameters and state keys (``step``, ``exp_avg``, ``exp_avg_sq``) as ``torch.optim.AdamW``; the moments are
+  created with ``zeros_like(param)`` so they are DTensors whenever the parameters are (DCP / FSDP2 optimizer checkpoints
+  see sharded state);
+* ``master_weights=True`` — the world_size-1 path, where the reference does not wrap the model in FSDP
+  (veomni/distributed/torch_parallelize.py:438-443,465): the constructor takes over the fp32 parameters as
+  ``state["master"]``, re-points every ``param.data`` at a bf16 copy the model computes on, and the kernel writes the
+  updated fp32 master *and* its bf16 rounding in the same pass (28 + 2 + 2 bytes per parameter, nothing else).
+
+No amsgrad, maximize, capturable or differentiable modes; CUDA only (anything else raises).
 """
 
 from __future__ import annotations
@@ -22,6 +31,7 @@ from . import _lib
 from ._lib import VB200Error, check, stream_ptr
 
 _ENTRY = 1 << 20
+_GRAD_DT = {torch.bfloat16: 0, torch.float32: 1}
 
 
 def _local(t: torch.Tensor) -> torch.Tensor:
@@ -30,26 +40,41 @@ def _local(t: torch.Tensor) -> torch.Tensor:
 
 class B200AdamW(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2):
+                 weight_decay: float = 1e-2, master_weights: bool = False):
         if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
             raise ValueError("invalid AdamW hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.master_weights = master_weights
         self._tables: dict = {}
+        if master_weights:
+            with torch.no_grad():
+                for group in self.param_groups:
+                    for p in group["params"]:
+                        if isinstance(p, DTensor) or not p.is_cuda or p.dtype != torch.float32:
+                            raise VB200Error("B200AdamW(master_weights=True) takes plain fp32 CUDA parameters")
+                        master = p.data
+                        self.state[p]["master"] = master
+                        p.data = master.to(torch.bfloat16)
+
+    @staticmethod
+    def _step_value(st) -> float:
+        s = st["step"]
+        return float(s.item()) if isinstance(s, torch.Tensor) else float(s)
 
     def _table(self, gi: int, tensors: list[list[torch.Tensor]]):
-        """Device pointer table for group ``gi``: rows = (param, grad, exp_avg, exp_avg_sq) pointers, last row numels;
-        rebuilt only when a pointer changed (gradients come back at the same addresses from the caching allocator)."""
+        """Device pointer table for group ``gi``: one row of pointers per tensor list, last row the entry sizes; rebuilt
+        only when a pointer changed (gradients come back at the same addresses from the caching allocator)."""
         key = tuple(t.data_ptr() for ts in tensors for t in ts)
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
-        rows = [[], [], [], [], []]
-        for p, g, m, v in zip(*tensors):
-            n = p.numel()
+        rows = [[] for _ in range(len(tensors) + 1)]
+        for ts in zip(*tensors):
+            n = ts[0].numel()
             for o in range(0, n, _ENTRY):
-                for r, t in zip(rows, (p, g, m, v)):
-                    r.append(t.data_ptr() + o * 4)
-                rows[4].append(min(_ENTRY, n - o))
+                for r, t in zip(rows, ts):
+                    r.append(t.data_ptr() + o * t.element_size())
+                rows[-1].append(min(_ENTRY, n - o))
         dev = tensors[0][0].device
         tab = torch.tensor(rows, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
         self._tables[gi] = (key, tab, len(rows[0]))
@@ -63,35 +88,47 @@ class B200AdamW(torch.optim.Optimizer):
                 loss = closure()
         lib = _lib.load()
         for gi, group in enumerate(self.param_groups):
-            ps, gs, ms, vs = [], [], [], []
+            ps, gs, ms, vs, lps = [], [], [], [], []
+            steps = set()
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                pl, gl = _local(p), _local(p.grad)
-                if not (pl.is_cuda and pl.dtype == torch.float32 and gl.dtype == torch.float32 and pl.is_contiguous()
-                        and gl.is_contiguous()):
-                    raise VB200Error("B200AdamW: contiguous fp32 CUDA parameters and gradients only")
                 st = self.state[p]
-                if not st:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(pl)
-                    st["exp_avg_sq"] = torch.zeros_like(pl)
+                if "exp_avg" not in st:
+                    like = st["master"] if self.master_weights else p
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)  # host tensor, as torch.optim.AdamW keeps it
+                    st["exp_avg"] = torch.zeros_like(like, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(like, memory_format=torch.preserve_format)
+                if not isinstance(st["step"], torch.Tensor):  # state dicts written by older versions / plain ints
+                    st["step"] = torch.tensor(float(st["step"]), dtype=torch.float32)
                 st["step"] += 1
-                ps.append(pl); gs.append(gl); ms.append(st["exp_avg"]); vs.append(st["exp_avg_sq"])
+                steps.add(self._step_value(st))
+                pl = st["master"] if self.master_weights else _local(p)
+                gl = _local(p.grad)
+                ml, vl = _local(st["exp_avg"]), _local(st["exp_avg_sq"])
+                if not (pl.is_cuda and pl.dtype == torch.float32 and pl.is_contiguous() and gl.is_contiguous()
+                        and gl.dtype in _GRAD_DT and gl.numel() == pl.numel() and ml.dtype == torch.float32):
+                    raise VB200Error("B200AdamW: contiguous fp32 CUDA parameters with fp32 or bf16 gradients only")
+                ps.append(pl); gs.append(gl); ms.append(ml); vs.append(vl)
+                if self.master_weights:
+                    lps.append(p.data)
             if not ps:
                 continue
-            steps = {self.state[p]["step"] for p in group["params"] if p.grad is not None}
             if len(steps) != 1:
                 raise VB200Error("B200AdamW: parameters of one group must share their step count")
+            if len({g.dtype for g in gs}) != 1:
+                raise VB200Error("B200AdamW: gradients of one group must share their dtype")
             t = steps.pop()
             b1, b2 = group["betas"]
-            tab, n = self._table(gi, [ps, gs, ms, vs])
+            lists = [ps, gs, ms, vs] + ([lps] if self.master_weights else [])
+            tab, n = self._table(gi, lists)
             gsd = None
             if grad_scale is not None:
                 gsd = grad_scale.to(device=ps[0].device, dtype=torch.float32).reshape(1).contiguous()
             with torch.cuda.device(ps[0].device):
                 check(lib.vb200_multi_adamw(tab[0].data_ptr(), tab[1].data_ptr(), tab[2].data_ptr(), tab[3].data_ptr(),
-                                            tab[4].data_ptr(), n, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                            tab[4].data_ptr() if self.master_weights else None, tab[-1].data_ptr(), n,
+                                            _GRAD_DT[gs[0].dtype], float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                             float(group["weight_decay"]), 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t),
                                             gsd.data_ptr() if gsd is not None else None, stream_ptr()), "vb200_multi_adamw")
         return loss

@@ -53,11 +53,18 @@ class ParallelState:
 
     @property
     def fsdp_mesh(self) -> DeviceMesh:
+        """Reference :253-268: a 2-D (replicate, shard) mesh under HSDP, the flattened shard mesh otherwise."""
+        if self.dp_replicate_size > 1:
+            if self.ulysses_size > 1 and self.dp_shard_size > 1:
+                return self.device_mesh["dp_replicate", "dp_shard_sp"]
+            return self.device_mesh["dp_replicate", "dp_shard"]
         return self.device_mesh["dp_shard_sp"]
 
     @property
     def fsdp_group(self):
-        return self.fsdp_mesh.get_group()
+        """The group parameters are sharded over (all-gather / reduce-scatter group)."""
+        m = self.fsdp_mesh
+        return m.get_group(m.ndim - 1) if m.ndim > 1 else m.get_group()
 
     @property
     def dp_group(self):

@@ -171,6 +171,27 @@ class SymmetricMemory:
             check(self._lib.vb200_allgather(self.comm, channel, self.offset_of(out), shard_numel * out.element_size(),
                                             num_ctas, _lib.stream_ptr()), "vb200_allgather")
 
+    def all_gather_scatter(self, out: torch.Tensor, shard_numel: int, table: list[int], channel: int,
+                           num_ctas: int = 32) -> None:
+        """All-gather with the copy-out fused in. ``out`` (in this region) only lends its slot ``rank`` (this rank's
+        shard row); ``table`` = n x (byte offset inside a shard row, shard bytes, destination pointer)."""
+        arr = (ctypes.c_int64 * len(table))(*[int(v) for v in table])
+        with torch.cuda.device(self.device):
+            check(self._lib.vb200_allgather_scatter(self.comm, channel, self.offset_of(out), shard_numel * out.element_size(),
+                                                    arr, len(table) // 3, num_ctas, _lib.stream_ptr()), "vb200_allgather_scatter")
+
+    def reduce_scatter_push_bf16(self, staging: torch.Tensor, desc: list[int], row: int, out: torch.Tensor, scale: float,
+                                 channel: int, num_ctas: int = 32) -> None:
+        """Reduce-scatter with the copy-in fused in. ``staging`` (in this region, >= world*row*2 bytes) receives the
+        peers' bf16 chunks; ``desc`` = n x (gradient pointer, numel, chunk elements)."""
+        if staging.numel() * staging.element_size() < self.world * row * 2:
+            raise VB200Error("reduce_scatter_push_bf16: staging buffer too small")
+        arr = (ctypes.c_int64 * len(desc))(*[int(v) for v in desc])
+        with torch.cuda.device(self.device):
+            check(self._lib.vb200_reduce_scatter_push_bf16(self.comm, channel, self.offset_of(staging), arr, len(desc) // 3,
+                                                           int(row), float(scale), out.data_ptr(), num_ctas,
+                                                           _lib.stream_ptr()), "vb200_reduce_scatter_push_bf16")
+
     def reduce_scatter_f32(self, inp: torch.Tensor, out: torch.Tensor, scale: float, channel: int,
                            num_ctas: int = 32) -> None:
         chunk = inp.numel() // self.world

@@ -18,6 +18,7 @@ from typing import Any
 import torch
 import torch.distributed as dist
 
+from . import prof
 from ._lib import VB200Error
 from .symm import SymmetricMemory, get_symmetric_memory
 
@@ -142,7 +143,9 @@ def all_to_all_many(xs: list[torch.Tensor], scatter_dim: int, gather_dim: int, g
         outs.append(out)
         off += sz
         base = buf
-    symm.all_to_all(base, descs, CH_ULYSSES, num_ctas)
+    moved = sum(x.numel() * x.element_size() for x in xs) * (world - 1) // world  # bytes this rank receives over NVLink
+    with prof.span("ulysses_a2a", moved):
+        symm.all_to_all(base, descs, CH_ULYSSES, num_ctas)
     return outs
 
 
