@@ -232,7 +232,11 @@ def run_b200(args) -> None:
         from veomni_b200.ep import EPContext
         from veomni_b200.parallel_state import get_parallel_state
 
-        vmoe.set_ep_group(EPContext(get_parallel_state().ep_group))
+        from veomni_b200.symm import get_symmetric_memory
+
+        ep_group = get_parallel_state().ep_group
+        # dispatch / combine staging: 4 buffers of T*K*H*2 = 134 MB each (grown 1.5x on demand) + the counts exchange
+        vmoe.set_ep_group(EPContext(ep_group, get_symmetric_memory(ep_group, 3 << 30)))
     fsdp = world > 1
     if args.torch_adamw:
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, fused=True)

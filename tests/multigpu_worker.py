@@ -353,6 +353,22 @@ def bench(symm, rank, world, dev):
         ms = timeit(lambda: symm.all_gather_inplace(out, U // world, 0, ctas))
         nbytes = (world - 1) / world * U * 2
         res.append({"kernel": f"fsdp_allgather[U=193M bf16,N={world},ctas={ctas}]", "ms": round(ms, 3), "nvlink_in_GBps": round(nbytes / ms / 1e6, 1)})
+    # the fused copy-out variant: Qwen3-8B layer parameter shapes, destinations in ordinary device memory
+    H, I, Hq, Hk, D = 4096, 12288, 32, 8, 128
+    shapes = [(Hq * D, H), (Hk * D, H), (Hk * D, H), (H, Hq * D), (D,), (D,), (I, H), (I, H), (H, I), (H,), (H,)]
+    numels = [(s_[0] + world - 1) // world * (s_[1] if len(s_) > 1 else 1) for s_ in shapes]
+    row = sum(numels)
+    buf = symm.empty((row * world,), torch.bfloat16, arena="fsdp_ag")
+    dsts = [torch.empty(n * world, dtype=torch.bfloat16, device=dev) for n in numels]
+    table, off = [], 0
+    for n, d in zip(numels, dsts):
+        table += [off * 2, n * 2, d.data_ptr()]
+        off += n
+    for ctas in (8, 16, 24, 32, 48, 64):
+        ms = timeit(lambda: symm.all_gather_scatter(buf, row, table, 0, ctas))
+        res.append({"kernel": f"fsdp_allgather+copy-out[Qwen3-8B layer unit,N={world},ctas={ctas}]", "ms": round(ms, 3),
+                    "nvlink_in_GBps": round((world - 1) * row * 2 / ms / 1e6, 1)})
+    del buf, dsts
     nc = torch.empty(U, dtype=torch.bfloat16, device=dev)
     ms = timeit(lambda: dist.all_gather_into_tensor(nc, nc[rank * (U // world) : (rank + 1) * (U // world)]))
     res.append({"kernel": f"(lib) nccl all_gather[U=193M bf16,N={world}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 2 / ms / 1e6, 1)})
@@ -365,6 +381,20 @@ def bench(symm, rank, world, dev):
     for ctas in (16, 32, 64):
         ms = timeit(lambda: symm.reduce_scatter_bf16(inp, U // world, o, 1.0 / world, 1, ctas))
         res.append({"kernel": f"fsdp_reducescatter_bf16pull[U=193M,N={world},ctas={ctas}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 2 / ms / 1e6, 1)})
+    # the fused copy-in variant: gradients read in place (bf16), pushed, reduced
+    from veomni_b200.fsdp_comm import pack_plan
+
+    grads = [torch.randn(*s_, device=dev, dtype=torch.bfloat16) for s_ in shapes]
+    plan, prow = pack_plan(shapes, world)
+    desc = []
+    for t, (numel, chunk, _o) in zip(grads, plan):
+        desc += [t.data_ptr(), numel, chunk]
+    o2 = torch.empty(prow, dtype=torch.float32, device=dev)
+    for ctas in (8, 16, 24, 32, 48, 64):
+        ms = timeit(lambda: symm.reduce_scatter_push_bf16(inp, desc, prow, o2, 1.0 / world, 1, ctas))
+        res.append({"kernel": f"fsdp_reducescatter push+reduce, copy-in fused[Qwen3-8B layer unit,N={world},ctas={ctas}]", "ms": round(ms, 3),
+                    "nvlink_out_GBps": round((world - 1) * prow * 2 / ms / 1e6, 1)})
+    del grads
     nci = torch.empty(U, dtype=torch.float32, device=dev)
     ms = timeit(lambda: dist.reduce_scatter_tensor(o, nci, op=dist.ReduceOp.AVG))
     res.append({"kernel": f"(lib) nccl reduce_scatter[U=193M fp32,N={world}]", "ms": round(ms, 3), "nvlink_in_GBps": round((world - 1) / world * U * 4 / ms / 1e6, 1)})

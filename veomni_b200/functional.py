@@ -126,10 +126,13 @@ class _AddRMSNorm(torch.autograd.Function):
         return dx, dx, dw.to(ctx.w_dtype), None
 
 
+FUSED_ADD_NORM_COLS = (1024, 2048, 4096, 5120, 8192)  # hidden sizes vb200_add_rmsnorm_fwd is instantiated for
+
+
 def fused_add_rms_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, eps: float):
     """``h = residual + x`` (bf16) and ``rms_norm(h, weight, eps)`` in one kernel; returns ``(normed, h)``.
     Replaces the `hidden_states = residual + hidden_states` + RMSNorm pair of the decoder layer
-    (patched_modeling_qwen3_gpu.py:369-375). Experimental: off by default in the callers."""
+    (patched_modeling_qwen3_gpu.py:369-375). Hidden sizes: ``FUSED_ADD_NORM_COLS``."""
     return _AddRMSNorm.apply(x, residual, weight, eps)
 
 

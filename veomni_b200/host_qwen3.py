@@ -151,7 +151,7 @@ class Qwen3DecoderLayer(nn.Module):
         self.mlp = Qwen3MLP(cfg)
         self.input_layernorm = Qwen3RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
         self.post_attention_layernorm = Qwen3RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
-        self.fuse_add_norm = os.environ.get("VB200_FUSE_ADD_NORM", "1") == "1"
+        self.fuse_add_norm = os.environ.get("VB200_FUSE_ADD_NORM", "1") == "1" and cfg.hidden_size in F.FUSED_ADD_NORM_COLS
 
     def forward(self, h, cos, sin, cu_seqlens, max_seqlen, sp_group=None, fwd_id=None):
         a = self.self_attn(self.input_layernorm(h), cos, sin, cu_seqlens, max_seqlen, sp_group, fwd_id)

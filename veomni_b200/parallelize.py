@@ -139,5 +139,11 @@ def build_parallelize_model(
         if experts and ps.ep_fsdp_size > 1:
             model._vb200_symm_ep = install_fsdp_comm(model, ps.ep_fsdp_device_mesh["ep_fsdp"].get_group(), num_ctas=comm_ctas,
                                                      rs_mode=rs_mode, fuse_copy_out=fuse_copy_out, modules=experts)
+    if ps.ep_enabled:
+        # fully_shard replaced every parameter by a new DTensor nn.Parameter: put the ExtraParallel tags back, the
+        # EP-aware gradient clip tells expert parameters apart by them (fsdp2/clip_grad_norm.py:60-75)
+        for fqn, p in model.named_parameters():
+            if fqn in model._fqn2spec_info:
+                p.spec_info = model._fqn2spec_info[fqn]
     _bind_clip(model)
     return model
