@@ -212,7 +212,9 @@ def run_b200(args) -> None:
         model = Qwen3MoeForCausalLM(cfg) if wl == "moe30b" else Qwen3ForCausalLM(cfg)
     reshard = bool(args.reshard)
     comm_kw = dict(b200_comm=not args.nccl_comm, comm_ctas=args.comm_ctas, rs_mode=args.rs_mode, fuse_copy_out=not args.no_fuse_copy_out,
-                   enable_reshard_after_forward=reshard)
+                   enable_reshard_after_forward=reshard,
+                   # Ulysses stages q/k/v (+ their gradients) of the local 32768/SP tokens in the symmetric region
+                   misc_bytes=(1536 << 20) if wl == "ulysses32k" else (256 << 20))
     if wl == "moe30b":
         # 30.5 B parameters never exist unsharded: slice / shard on the meta device, then materialise and initialise the shards
         model = build_parallelize_model(model, init_device="meta", **comm_kw)
@@ -236,7 +238,7 @@ def run_b200(args) -> None:
 
         ep_group = get_parallel_state().ep_group
         # dispatch / combine staging: 4 buffers of T*K*H*2 = 134 MB each (grown 1.5x on demand) + the counts exchange
-        vmoe.set_ep_group(EPContext(ep_group, get_symmetric_memory(ep_group, 3 << 30)))
+        vmoe.set_ep_group(EPContext(ep_group, get_symmetric_memory(ep_group, 3 << 30, tag="ep")))
     fsdp = world > 1
     if args.torch_adamw:
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.95), weight_decay=0.0, fused=True)

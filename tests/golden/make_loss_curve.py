@@ -7,7 +7,7 @@ Run in the authoring container only (needs /root/reference):
 What runs is the reference, unmodified, through its own entry point for tests
 (``/root/reference/tests/train_scripts/train_text_test.py`` -> ``TextTrainer`` -> ``build_foundation_model`` ->
 ``build_parallelize_model`` (FSDP2, 2 ranks) -> ``veomni_clip_grad_norm`` -> AdamW) on CPU / gloo with the shim documented
-in SURVEY.md Appendix B (gloo backend, ``torch.cpu`` memory-stat stubs, nothing else), all ops eager, attention sdpa.
+in SURVEY.md Appendix B (gloo backend, ``torch.cpu`` memory-stat stubs, a per-sequence SDPA in the flash-attn slot), all ops eager.
 Two runs: FSDP2 mixed precision bf16 params / fp32 reduce (the reference's default,
 veomni/arguments/arguments_types.py:241-263) and the same with ``param_dtype=float32``, which bounds how much of any
 difference is bf16 rounding rather than algorithm.
@@ -77,6 +77,27 @@ def worker():
         return orig_fb(self, micro_batch)
 
     tb.BaseTrainer.forward_backward_step = fb
+    # Packed micro-batches: the GPU path of the reference is flash-attn varlen driven by cu_seq_lens (block-diagonal causal
+    # attention, veomni/ops/kernels/attention/__init__.py:282-320). flash-attn does not exist on CPU, so the run keeps
+    # attn_implementation=flash_attention_2 — VeOmni's own wrapper and kwargs plumbing — and fills the documented slot
+    # `_flash_attention_forward` (:33-37) with a per-sequence SDPA of the same semantics. HF's plain
+    # "sdpa" path would NOT do: given the collator's all-ones attention_mask it attends across the samples of a pack.
+    import torch.nn.functional as F
+
+    import veomni.ops.kernels.attention as A
+
+    def cpu_varlen(query, key, value, attention_mask, query_length=None, is_causal=True, dropout=0.0, softmax_scale=None,
+                   cu_seq_lens_q=None, cu_seq_lens_k=None, **kw):  # q/k/v: [B, S, H, D]
+        out = torch.empty_like(query)
+        Hq, Hk = query.shape[2], key.shape[2]
+        cu = cu_seq_lens_q.tolist() if cu_seq_lens_q is not None else [0, query.shape[1]]
+        for a, b in zip(cu[:-1], cu[1:]):
+            q, k, v = (t[:, a:b].transpose(1, 2) for t in (query, key, value))
+            k, v = k.repeat_interleave(Hq // Hk, 1), v.repeat_interleave(Hq // Hk, 1)
+            out[:, a:b] = F.scaled_dot_product_attention(q, k, v, is_causal=is_causal, scale=softmax_scale).transpose(1, 2)
+        return out
+
+    A._flash_attention_forward = cpu_varlen
     orig_end = tb.BaseTrainer.on_step_end
 
     def on_end(self, loss=None, loss_dict=None, grad_norm=None):
@@ -101,7 +122,7 @@ def worker():
 def run_reference(tmp: Path, data_dir: Path, cfg_dir: Path, steps: int, mixed: bool) -> list:
     out = tmp / ("bf16" if mixed else "fp32")
     out.mkdir()
-    eager = ["attn_implementation=sdpa", "moe_implementation=eager", "cross_entropy_loss_implementation=eager",
+    eager = ["attn_implementation=flash_attention_2", "moe_implementation=eager", "cross_entropy_loss_implementation=eager",
              "rms_norm_implementation=eager", "swiglu_mlp_implementation=eager", "rotary_pos_emb_implementation=eager",
              "load_balancing_loss_implementation=eager", "rms_norm_gated_implementation=eager",
              "causal_conv1d_implementation=eager", "chunk_gated_delta_rule_implementation=eager"]

@@ -61,6 +61,22 @@ def bench_attention(dev, iters):
     except Exception as ex:  # noqa: BLE001
         print({"attn_bwd_tcgen05_pp": str(ex)})
     A.BWD_PP = not A.BWD_PP
+    for p16 in (False, True):
+        A.BWD_P16 = p16
+        try:
+            report(f"attn_fwd+bwd_tcgen05 (BWD_P16={p16})[4096,32/8,128,causal]", time_fn(fb, gsets, iters), flops=flops_fwd * 3.5)
+            qg, kg, vg = gsets[0]
+            o = flash_attn_varlen(qg, kg, vg, cu, T)
+
+            def bwd_only():
+                o.backward(do, retain_graph=True)
+                qg.grad = kg.grad = vg.grad = None
+
+            report(f"attn_bwd only (delta + dQ + dK/dV) (BWD_P16={p16})[4096,32/8,128,causal]", time_fn(lambda: bwd_only(), [()], iters),
+                   flops=flops_fwd * 2.5)
+        except Exception as ex:  # noqa: BLE001
+            print({"attn_bwd_p16": str(ex)})
+    A.BWD_P16 = False
     A.FWD_IMPL, A.BWD_IMPL = old2
     try:
         from flash_attn import flash_attn_varlen_func

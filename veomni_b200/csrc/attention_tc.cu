@@ -349,8 +349,13 @@ enum { Q_LOAD = 0, Q_KFULL = 1, Q_VFULL = Q_KFULL + TB_KV_MAX, Q_KEMPTY = Q_VFUL
 // PP = true ("ping-pong"): the two softmax warpgroups (warps 2-5 / 6-9) take alternate K/V tiles — each thread does
 // all 64 columns of its row for its tiles and owns one S/dP buffer — instead of all eight warps splitting the columns
 // of the same tile and then waiting together for the next S: while one warpgroup waits for its MMAs the other computes.
-template <bool TS, bool PP>
-__global__ void __launch_bounds__(320, 1)
+// P16 = true (implies TS, !PP): SIXTEEN softmax warps in two groups of eight. A group works like the eight warps of the
+// default kernel (warps w and w+4 of the group share a TMEM lane quadrant and take one 32-column chunk each) but the two
+// groups take alternate K/V tiles, each owning one S/dP/dS buffer: the per-tile chain wait -> tcgen05.ld -> exponentials ->
+// store -> fence -> arrive (~2000 clk in the default kernel against 770-1140 clk of MMA, the softmax warps never idle) runs
+// twice concurrently, with four warps per scheduler instead of two to hide its latencies.
+template <bool TS, bool PP, bool P16 = false>
+__global__ void __launch_bounds__(P16 ? 576 : 320, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const AttnTcBwdParams p) {
@@ -378,7 +383,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (int i = 0; i < Q_COUNT; ++i) {
             const bool by_warps = (i >= Q_SEMPTY && i < Q_SEMPTY + 2) || (i >= Q_DSFULL && i < Q_DSFULL + 2) ||
                                   (TS && i == Q_LOAD);
-            mbar_init(&bar[i], by_warps ? ((PP && i != Q_LOAD) ? 4 : 8) : 1);
+            mbar_init(&bar[i], by_warps ? ((PP && i != Q_LOAD) ? 4 : 8) : 1);  // P16: 8 warps per group / per barrier
         }
         mbar_fence_init();
     }
@@ -473,8 +478,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
     } else {
         // 8 softmax warps: warps w and w+4 share TMEM lane quadrant (w & 3) and split the tile's two 32-column chunks
+        static_assert(!P16 || (TS && !PP), "P16 builds on the TMEM-operand kernel and replaces PP");
         const int q = warp & 3;
-        const int cw = (warp - 2) >> 2;  // column chunk of this warp
+        const int grp = P16 ? (warp - 2) >> 3 : 0;   // P16: softmax group (alternate tiles)
+        const int cw = ((warp - 2) >> 2) & 1;        // column chunk of this warp
         const int r = q * 32 + lane;
         const int m = m0 + r;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
@@ -485,7 +492,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             lse2 = (l == -INFINITY) ? 0.f : l * kLog2eTc;
             dl = p.delta[(int64_t)h * p.total + s0 + m];
         }
-        if (TS) {
+        if (TS && grp == 0) {
             // this thread's Q row (warps 2-5) or dO row (warps 6-9): 256 contiguous bytes, global -> registers -> TMEM;
             // two bf16 per 32-bit column is exactly the K-major A-operand layout
             const __nv_bfloat16* src = cw == 0 ? p.q + (int64_t)(s0 + m) * p.q_st + (int64_t)h * p.q_sh
@@ -507,7 +514,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar[Q_LOAD]);
         }
-        for (int j = PP ? cw : 0; j < n_tiles; j += PP ? 2 : 1) {
+        for (int j = P16 ? grp : (PP ? cw : 0); j < n_tiles; j += (PP || P16) ? 2 : 1) {
             const int st = j & 1;
             const uint32_t ph = (uint32_t)(j >> 1) & 1u;
             mbar_wait(&bar[Q_SPFULL + st], ph);
@@ -566,7 +573,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc_fence_after();
         __nv_bfloat16* row = p.dq + (int64_t)(s0 + m) * p.dq_st + (int64_t)h * p.dq_sh;
 #pragma unroll 1
-        for (int c = cw * 2; c < cw * 2 + 2; ++c) {
+        for (int c = P16 ? grp * 2 + cw : cw * 2; c < (P16 ? grp * 2 + cw + 1 : cw * 2 + 2); ++c) {
             uint32_t v[32];
             tmem_ld32(lane_base + 256 + c * 32, v);
             if (m < L) {
@@ -602,8 +609,10 @@ enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = K_QFULL + TB_QS_MAX, K_STFULL = K_QEM
 // stores and the 32 KB of A reads per tile, the proxy fence, and frees 64 KB for a deeper Q/dO ring. No extra
 // synchronisation is needed for the aliasing: S^T_{j+2} is issued after dV/dK_j and tcgen05.mma executes in issue order.
 
-template <bool TS, bool PP>  // PP: the two softmax warpgroups take alternate (head, q tile) jobs, see the dQ kernel
-__global__ void __launch_bounds__(320, 1)
+// P16 (implies TS, !PP): sixteen softmax warps in two groups of eight on alternate jobs, as in the dQ kernel; each thread then
+// works on 16-column halves of its chunk (tcgen05.ld/st .x16/.x8) so that 576 threads fit the register file.
+template <bool TS, bool PP, bool P16 = false>  // PP: the two softmax warpgroups take alternate (head, q tile) jobs, see the dQ kernel
+__global__ void __launch_bounds__(P16 ? 576 : 320, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                         const AttnTcBwdParams p) {
@@ -619,6 +628,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + K_COUNT);
     float* sStat = reinterpret_cast<float*>(tmem_slot + 4);  // [2 stages (PP: 2 warpgroups x 2)][lse2 x64 | delta x64]
     static_assert(!PP || TS, "the ping-pong variant is built on the TMEM-operand kernel");
+    static_assert(!P16 || (TS && !PP), "P16 builds on the TMEM-operand kernel and replaces PP");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int order, hk, seq;
     tile_of_block(p.Hk, p.nseq, order, hk, seq);
@@ -733,10 +743,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
     } else {
         // 8 softmax warps: warps w and w+4 share TMEM lane quadrant (w & 3) and split the tile's two 32-column chunks
         const int q = warp & 3;
-        const int cw = (warp - 2) >> 2;
+        const int grp = P16 ? (warp - 2) >> 3 : 0;  // P16: softmax group (alternate jobs)
+        const int cw = ((warp - 2) >> 2) & 1;
         const int r = q * 32 + lane;
         const int tid = PP ? ((warp - 2) & 3) * 32 + lane   // 0..127 inside this warpgroup
-                           : (warp - 2) * 32 + lane;       // 0..255 over the softmax warps
+                           : ((warp - 2) & 7) * 32 + lane;  // 0..255 over the (group's) eight softmax warps
         const int n = n0 + r;  // kv index of this thread's row
         // per-column statistics of the first job are fetched up front; each later job's are prefetched one job ahead
         auto load_stat = [&](int jb) -> float {
@@ -751,20 +762,21 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             }
             return -p.delta[(int64_t)hh * p.total + s0 + mm];
         };
-        float stat_next = load_stat(PP ? cw : 0);
+        float stat_next = load_stat(P16 ? grp : (PP ? cw : 0));
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         const float sl2 = p.scale * kLog2eTc;
-        for (int jb = PP ? cw : 0; jb < jobs; jb += PP ? 2 : 1) {
+        for (int jb = P16 ? grp : (PP ? cw : 0); jb < jobs; jb += (PP || P16) ? 2 : 1) {
             const int st = jb & 1;
             const uint32_t ph = (uint32_t)(jb >> 1) & 1u;
             const int qi = i_start + jb % nq;
             // per-column (q index) softmax statistics of this q tile: 64 lse2 + 64 delta values through smem
             // (PP: a strip pair per warpgroup, alternating with the warpgroup's job count)
-            float* strip = sStat + (PP ? (cw * 2 + (int)ph) : st) * 128;
+            float* strip = sStat + (P16 ? (grp * 2 + (int)ph) : PP ? (cw * 2 + (int)ph) : st) * 128;
             if (tid < 128) strip[tid] = stat_next;
             if (PP) asm volatile("bar.sync %0, 128;" ::"r"(1 + cw) : "memory");  // this warpgroup only
+            else if (P16) asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");  // this group's eight warps
             else asm volatile("bar.sync 1, 256;" ::: "memory");                  // the 8 softmax warps only
-            stat_next = load_stat(jb + (PP ? 2 : 1));
+            stat_next = load_stat(jb + ((PP || P16) ? 2 : 1));
             const float* lse_s = strip;
             const float* dl_s = lse_s + 64;
             mbar_wait(&bar[K_STFULL + st], ph);
@@ -772,6 +784,54 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
             if (!TS) mbar_wait(&bar[K_PEMPTY + st], ph ^ 1);
             const uint32_t pt_a = smem_u32(sPt + st * TB_DS), dst_a = smem_u32(sdSt + st * TB_DS);
             const bool need_mask = (qi * TB_N + TB_N > L) || (n0 + TC_BM > L) || (p.causal && n0 + TC_BM > qi * TB_N);
+            if (P16) {
+                // two 16-column halves of this warp's 32-column chunk; P^T / dS^T go back over columns the chunk has
+                // already given up (packed: half h lands on columns [c*32 + 8h, +8), all of them read in half 0)
+                const int c = cw;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t sv[16], dv[16], pk[8], dk[8];
+                    tmem_ld16_nowait(lane_base + st * TB_N + c * 32 + hf * 16, sv);
+                    tmem_ld16_nowait(lane_base + 128 + st * TB_N + c * 32 + hf * 16, dv);
+                    tmem_wait_ld();
+                    const int c0 = c * 32 + hf * 16;
+                    if (need_mask) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            float pe[2], de[2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int m = qi * TB_N + c0 + i + e;  // q index (column)
+                                const bool ok = n < L && m < L && (!p.causal || n <= m);
+                                pe[e] = ok ? exp2f(__uint_as_float(sv[i + e]) * sl2 + lse_s[c0 + i + e]) : 0.f;
+                                de[e] = pe[e] * (__uint_as_float(dv[i + e]) + dl_s[c0 + i + e]);
+                            }
+                            pk[i >> 1] = f2_to_bf2(pe[0], pe[1]);
+                            dk[i >> 1] = f2_to_bf2(de[0], de[1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c0 + i);
+                            const float4 d4 = *reinterpret_cast<const float4*>(dl_s + c0 + i);
+                            const float2 sl2v = make_float2(sl2, sl2);
+                            const float2 t0 = ffma2(make_float2(__uint_as_float(sv[i + 0]), __uint_as_float(sv[i + 1])), sl2v, make_float2(l4.x, l4.y));
+                            const float2 t1 = ffma2(make_float2(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])), sl2v, make_float2(l4.z, l4.w));
+                            const float2 e0 = make_float2(exp2f(t0.x), exp2f(t0.y)), e1 = make_float2(exp2f(t1.x), exp2f(t1.y));
+                            const float2 u0 = fadd2(make_float2(__uint_as_float(dv[i + 0]), __uint_as_float(dv[i + 1])), make_float2(d4.x, d4.y));
+                            const float2 u1 = fadd2(make_float2(__uint_as_float(dv[i + 2]), __uint_as_float(dv[i + 3])), make_float2(d4.z, d4.w));
+                            const float2 w0 = fmul2(e0, u0), w1 = fmul2(e1, u1);
+                            pk[i >> 1] = f2_to_bf2(e0.x, e0.y);
+                            pk[(i >> 1) + 1] = f2_to_bf2(e1.x, e1.y);
+                            dk[i >> 1] = f2_to_bf2(w0.x, w0.y);
+                            dk[(i >> 1) + 1] = f2_to_bf2(w1.x, w1.y);
+                        }
+                    }
+                    tmem_st8(lane_base + st * TB_N + c * 32 + hf * 8, pk);
+                    tmem_st8(lane_base + 128 + st * TB_N + c * 32 + hf * 8, dk);
+                }
+                tmem_wait_st();
+            } else
 #pragma unroll 1
             for (int c = PP ? 0 : cw; c < (PP ? 2 : cw + 1); ++c) {
                 uint32_t sv[32], dv[32];
@@ -843,7 +903,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_co
         __nv_bfloat16* vrow = p.dv + (int64_t)(s0 + n) * p.dv_st + (int64_t)hk * p.dv_sh;
         __nv_bfloat16* krow = p.dk + (int64_t)(s0 + n) * p.dk_st + (int64_t)hk * p.dk_sh;
 #pragma unroll 1
-        for (int c = cw * 2; c < cw * 2 + 2; ++c) {
+        for (int c = P16 ? grp * 2 + cw : cw * 2; c < (P16 ? grp * 2 + cw + 1 : cw * 2 + 2); ++c) {
             uint32_t v[32], kk[32];
             tmem_ld32(lane_base + 256 + c * 32, v);
             tmem_ld32(lane_base + 384 + c * 32, kk);
@@ -926,6 +986,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     const int only = (causal >> 8) & 3;
     const bool ss_operands = (causal >> 10) & 1;  // bit 10: all MMA operands from shared memory (cross-check variant)
     const bool pingpong = (causal >> 11) & 1;     // bit 11: softmax warpgroups on alternate tiles
+    const bool p16 = (causal >> 12) & 1;          // bit 12: sixteen softmax warps, two groups of eight on alternate tiles
     causal &= 1;
     if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: head_dim must be 128");
     if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: Hq % Hk != 0");
@@ -962,6 +1023,8 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq_ts));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
         attr = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -970,6 +1033,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     dim3 gq(p.tiles * q_heads * num_seqs);
     if (only != 2) {
         if (ss_operands) attn_bwd_dq_tc_kernel<false, false><<<gq, 320, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        else if (p16) attn_bwd_dq_tc_kernel<true, false, true><<<gq, 576, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         else if (pingpong) attn_bwd_dq_tc_kernel<true, true><<<gq, 320, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         else attn_bwd_dq_tc_kernel<true, false><<<gq, 320, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         vb200_count_launch(1);
@@ -978,6 +1042,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     dim3 gk(p.tiles * k_heads * num_seqs);
     if (only != 1) {
         if (ss_operands) attn_bwd_dkdv_tc_kernel<false, false><<<gk, 320, smem_kv, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
+        else if (p16) attn_bwd_dkdv_tc_kernel<true, false, true><<<gk, 576, smem_kv_ts, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
         else if (pingpong) attn_bwd_dkdv_tc_kernel<true, true><<<gk, 320, smem_kv_ts, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
         else attn_bwd_dkdv_tc_kernel<true, false><<<gk, 320, smem_kv_ts, s>>>(tmK128, tmV128, tmQ64, tmdO64, p);
         vb200_count_launch(1);

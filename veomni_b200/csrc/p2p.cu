@@ -553,21 +553,25 @@ struct ScatterArgs {
     uint8_t* dst[kScatterMax];           // the parameter's unsharded tensor (local memory, world * bytes)
 };
 
+constexpr int kTileVecs = 8;  // 16-byte vectors per thread per tile: a tile is blockDim * 8 * 16 B = 64 KB of one parameter
+
 __global__ void __launch_bounds__(512)
 allgather_scatter_kernel(CommDev c, int ch, int64_t off, int64_t shard_bytes, ScatterArgs a) {
     __shared__ int64_t peer_off[kMaxWorld];
-    __shared__ int64_t s_prefix[kScatterMax + 1];  // 16-byte vectors before parameter i inside a row
+    __shared__ int s_tprefix[kScatterMax + 1];  // 64 KB tiles before parameter i inside one rank's row
     __shared__ int64_t s_off[kScatterMax], s_bytes[kScatterMax];
     __shared__ uint8_t* s_dst[kScatterMax];
+    __shared__ const uint8_t* s_base[kMaxWorld];
     const uint32_t e = c.state[ch] + 1;
     if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);
+    const int64_t tile_bytes = (int64_t)blockDim.x * kTileVecs * 16;
     if (threadIdx.x == 0) {
-        int64_t acc = 0;
+        int acc = 0;
         for (int i = 0; i < a.n; ++i) {
-            s_prefix[i] = acc;
-            acc += a.bytes[i] >> 4;
+            s_tprefix[i] = acc;
+            acc += (int)((a.bytes[i] + tile_bytes - 1) / tile_bytes);
         }
-        s_prefix[a.n] = acc;
+        s_tprefix[a.n] = acc;
     }
     for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
         s_off[i] = a.off[i];
@@ -575,34 +579,41 @@ allgather_scatter_kernel(CommDev c, int ch, int64_t off, int64_t shard_bytes, Sc
         s_dst[i] = a.dst[i];
     }
     wait_peers(c, ch, 0, e, peer_off);  // ends with a block-wide barrier
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-    for (int q = 0; q < c.world; ++q) {
-        const int p = (c.rank + q) % c.world;  // q = 0: this rank's own shard; sources staggered over the peers
-        const uint8_t* src = c.data[p] + peer_off[p] + (int64_t)p * shard_bytes;
-        if (a.vec_ok) {
-            const int64_t vrow = s_prefix[a.n];
-            constexpr int UN = 8;  // independent 16-byte peer loads in flight per thread
-            for (int64_t v0 = tid; v0 < vrow; v0 += nthr * UN) {
-                uint4 r[UN];
-                uint4* d[UN];
+    if ((int)threadIdx.x < c.world) s_base[threadIdx.x] = c.data[threadIdx.x] + peer_off[threadIdx.x] + (int64_t)threadIdx.x * shard_bytes;
+    __syncthreads();
+    if (a.vec_ok) {
+        // Work = (peer q, 64 KB tile of one parameter). A CTA walks the tiles of a peer with stride gridDim, so the
+        // parameter index only ever moves forward (no per-vector search: the copy itself is ~3 instructions per
+        // 16 bytes and must stay that cheap for 32 CTAs to keep the links busy); every thread has 8 independent
+        // 16-byte peer loads in flight, then stores them.
+        const int tiles_per_peer = s_tprefix[a.n];
+        for (int q = 0; q < c.world; ++q) {
+            const int p = (c.rank + q) % c.world;  // q = 0: this rank's own shard; sources staggered over the peers
+            const uint8_t* src_row = s_base[p];
+            int i = 0;
+            for (int t = blockIdx.x; t < tiles_per_peer; t += gridDim.x) {
+                while (t >= s_tprefix[i + 1]) ++i;
+                const int64_t base = (int64_t)(t - s_tprefix[i]) * tile_bytes;
+                const int64_t left = s_bytes[i] - base;  // > 0
+                const uint8_t* src = src_row + s_off[i] + base;
+                uint8_t* dst = s_dst[i] + (int64_t)p * s_bytes[i] + base;
+                uint4 r[kTileVecs];
 #pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const int64_t v = v0 + (int64_t)u * nthr;
-                    d[u] = nullptr;
-                    if (v < vrow) {
-                        const int i = find_segment(s_prefix, a.n, v);
-                        const int64_t k = (v - s_prefix[i]) << 4;
-                        r[u] = ldg_v4(src + s_off[i] + k);
-                        d[u] = reinterpret_cast<uint4*>(s_dst[i] + (int64_t)p * s_bytes[i] + k);
-                    }
+                for (int u = 0; u < kTileVecs; ++u) {
+                    const int64_t o = ((int64_t)u * blockDim.x + threadIdx.x) << 4;
+                    if (o < left) r[u] = ldg_v4(src + o);
                 }
 #pragma unroll
-                for (int u = 0; u < UN; ++u)
-                    if (d[u]) stg_v4(d[u], r[u]);
+                for (int u = 0; u < kTileVecs; ++u) {
+                    const int64_t o = ((int64_t)u * blockDim.x + threadIdx.x) << 4;
+                    if (o < left) stg_v4(dst + o, r[u]);
+                }
             }
-        } else {
-            for (int i = 0; i < a.n; ++i) grid_copy(s_dst[i] + (int64_t)p * s_bytes[i], src + s_off[i], s_bytes[i]);
+        }
+    } else {
+        for (int q = 0; q < c.world; ++q) {
+            const int p = (c.rank + q) % c.world;
+            for (int i = 0; i < a.n; ++i) grid_copy(s_dst[i] + (int64_t)p * s_bytes[i], s_base[p] + s_off[i], s_bytes[i]);
         }
     }
     if (grid_arrive_last(c, ch)) finish_epoch(c, ch, e);
@@ -640,16 +651,22 @@ reduce_scatter_push_bf16_kernel(CommDev c, int ch, int64_t off, PushArgs a, floa
     __shared__ int64_t s_prefix[kPushMax + 1];  // element offset of parameter i inside a row
     __shared__ const __nv_bfloat16* s_src[kPushMax];
     __shared__ int64_t s_numel[kPushMax], s_chunk[kPushMax];
+    __shared__ int s_tprefix[kPushMax + 1];  // 64 KB tiles before parameter i inside one row
     __shared__ int s_last;
     const uint32_t e = c.state[ch] + 1;
     if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);  // "my staging buffer (at off) is free for epoch e"
     if (threadIdx.x == 0) {
         int64_t acc = 0;
+        int tacc = 0;
+        const int64_t tile_elems = (int64_t)blockDim.x * kTileVecs * 8;
         for (int i = 0; i < a.n; ++i) {
             s_prefix[i] = acc;
+            s_tprefix[i] = tacc;
             acc += a.chunk[i];
+            tacc += (int)((a.chunk[i] + tile_elems - 1) / tile_elems);
         }
         s_prefix[a.n] = acc;
+        s_tprefix[a.n] = tacc;
     }
     for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
         s_src[i] = a.src[i];
@@ -661,38 +678,49 @@ reduce_scatter_push_bf16_kernel(CommDev c, int ch, int64_t off, PushArgs a, floa
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
     const int64_t row = a.row;
     // ---- phase A: push -------------------------------------------------------------------------------------------
-    for (int q = 0; q < c.world; ++q) {
-        const int p = (c.rank + q) % c.world;  // q = 0: own chunk into the local staging slot
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.data[p] + peer_off[p]) + (int64_t)c.rank * row;
-        if (a.vec_ok) {
-            const int64_t nvec = row >> 3;
-            constexpr int UN = 4;
-            for (int64_t v0 = tid; v0 < nvec; v0 += nthr * UN) {
-                uint4 r[UN];
+    // Work = (peer q, 64 KB tile of one parameter's chunk), walked like the all-gather's tiles: no per-vector search.
+    if (a.vec_ok) {
+        const int64_t tile_elems = (int64_t)blockDim.x * kTileVecs * 8;
+        const int tiles_per_peer = s_tprefix[a.n];
+        for (int q = 0; q < c.world; ++q) {
+            const int p = (c.rank + q) % c.world;  // q = 0: own chunk into the local staging slot
+            __nv_bfloat16* dst_row = reinterpret_cast<__nv_bfloat16*>(c.data[p] + peer_off[p]) + (int64_t)c.rank * row;
+            int i = 0;
+            for (int t = blockIdx.x; t < tiles_per_peer; t += gridDim.x) {
+                while (t >= s_tprefix[i + 1]) ++i;
+                const int64_t base = (int64_t)(t - s_tprefix[i]) * tile_elems;  // element inside the chunk
+                const int64_t left = s_chunk[i] - base;                          // elements of the chunk from here on
+                const int64_t g0 = (int64_t)p * s_chunk[i] + base;               // element of gradient i
+                const __nv_bfloat16* src = s_src[i];
+                const int64_t numel = s_numel[i];
+                __nv_bfloat16* dst = dst_row + s_prefix[i] + base;
+                uint4 r[kTileVecs];
 #pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const int64_t v = v0 + (int64_t)u * nthr;
-                    if (v < nvec) {
-                        const int64_t x = v << 3;
-                        const int i = find_segment(s_prefix, a.n, x);
-                        const int64_t g = (int64_t)p * s_chunk[i] + (x - s_prefix[i]);  // element of gradient i
-                        if (g + 8 <= s_numel[i]) {
-                            r[u] = ldg_stream(s_src[i] + g);
+                for (int u = 0; u < kTileVecs; ++u) {
+                    const int64_t x = ((int64_t)u * blockDim.x + threadIdx.x) << 3;
+                    if (x < left) {
+                        const int64_t g = g0 + x;
+                        if (g + 8 <= numel) {
+                            r[u] = ldg_stream(src + g);
                         } else {  // dim-0 padding: zeros
-                            __align__(16) __nv_bfloat16 t[8];
+                            __align__(16) __nv_bfloat16 tv[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) t[j] = g + j < s_numel[i] ? s_src[i][g + j] : __float2bfloat16_rn(0.f);
-                            r[u] = *reinterpret_cast<uint4*>(t);
+                            for (int j = 0; j < 8; ++j) tv[j] = g + j < numel ? src[g + j] : __float2bfloat16_rn(0.f);
+                            r[u] = *reinterpret_cast<uint4*>(tv);
                         }
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < UN; ++u) {
-                    const int64_t v = v0 + (int64_t)u * nthr;
-                    if (v < nvec) stg_v4(dst + (v << 3), r[u]);
+                for (int u = 0; u < kTileVecs; ++u) {
+                    const int64_t x = ((int64_t)u * blockDim.x + threadIdx.x) << 3;
+                    if (x < left) stg_v4(dst + x, r[u]);
                 }
             }
-        } else {
+        }
+    } else {
+        for (int q = 0; q < c.world; ++q) {
+            const int p = (c.rank + q) % c.world;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c.data[p] + peer_off[p]) + (int64_t)c.rank * row;
             for (int64_t x = tid; x < row; x += nthr) {
                 const int i = find_segment(s_prefix, a.n, x);
                 const int64_t g = (int64_t)p * s_chunk[i] + (x - s_prefix[i]);

@@ -369,7 +369,8 @@ def _patch_copy_in() -> None:
         fc._get_param_all_gather_inputs = _param_all_gather_inputs
 
 
-def plan_fsdp_region(model: torch.nn.Module, world: int, param_bytes: int = 2, reduce_bytes: int = 4, modules=None):
+def plan_fsdp_region(model: torch.nn.Module, world: int, param_bytes: int = 2, reduce_bytes: int = 4, modules=None,
+                     misc_bytes: int = 256 << 20):
     """Size the symmetric region from the FSDP2 unit sizes of ``model``.
 
     Live all-gather outputs: the unit being copied out + the prefetched one; live reduce-scatter inputs:
@@ -400,14 +401,14 @@ def plan_fsdp_region(model: torch.nn.Module, world: int, param_bytes: int = 2, r
     slack = 64 << 20
     ag = (top + 2 * second) * param_bytes + slack
     rs = (top + 2 * second) * reduce_bytes + slack
-    misc = 256 << 20
+    misc = int(misc_bytes)  # everything that is not an FSDP buffer: Ulysses / EP staging, self-check scratch
     total = ag + rs + misc
     return total, {"fsdp_ag": ag / total, "fsdp_rs": rs / total, "misc": misc / total}
 
 
 def install_fsdp_comm(model: torch.nn.Module, group: dist.ProcessGroup | None = None, symm: SymmetricMemory | None = None,
                       num_ctas: int = 32, pack_bf16: bool = True, rs_mode: str | None = None,
-                      fuse_copy_out: bool = True, modules=None) -> SymmetricMemory:
+                      fuse_copy_out: bool = True, modules=None, misc_bytes: int = 256 << 20) -> SymmetricMemory:
     """Swap every FSDP2 unit of ``model`` onto the NVLink collectives.
 
     Call right after ``build_parallelize_model`` returns (veomni/trainer/base.py:387-404). ``rs_mode``: "push" (default:
@@ -420,7 +421,7 @@ def install_fsdp_comm(model: torch.nn.Module, group: dist.ProcessGroup | None = 
 
     if symm is None:
         g = group if group is not None else dist.group.WORLD
-        total, arenas = plan_fsdp_region(model, dist.get_world_size(g), modules=modules)
+        total, arenas = plan_fsdp_region(model, dist.get_world_size(g), modules=modules, misc_bytes=misc_bytes)
         symm = get_symmetric_memory(g, total, arenas)
     ag = B200AllGather(symm, num_ctas, fuse_copy_out)
     rs = B200ReduceScatter(symm, num_ctas, pack_bf16, rs_mode)

@@ -60,6 +60,7 @@ def build_parallelize_model(
     fuse_copy_out: bool = True,
     init_device: str | None = None,
     enable_forward_prefetch: bool = True,
+    misc_bytes: int = 256 << 20,
 ) -> torch.nn.Module:
     ps = get_parallel_state()
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -135,7 +136,7 @@ def build_parallelize_model(
         experts = [m for m in ep_modules.values() if isinstance(m, FSDPModule)]
         if dist.get_world_size(shard_group) > 1:
             model._vb200_symm = install_fsdp_comm(model, shard_group, num_ctas=comm_ctas, rs_mode=rs_mode,
-                                                  fuse_copy_out=fuse_copy_out, modules=dense)
+                                                  fuse_copy_out=fuse_copy_out, modules=dense, misc_bytes=misc_bytes)
         if experts and ps.ep_fsdp_size > 1:
             model._vb200_symm_ep = install_fsdp_comm(model, ps.ep_fsdp_device_mesh["ep_fsdp"].get_group(), num_ctas=comm_ctas,
                                                      rs_mode=rs_mode, fuse_copy_out=fuse_copy_out, modules=experts)

@@ -228,14 +228,16 @@ class SymmetricMemory:
             self._lib.vb200_symm_free(self._base)
 
 
-_default: dict[int, SymmetricMemory] = {}
+_default: dict[tuple, SymmetricMemory] = {}
 
 
 def get_symmetric_memory(group: dist.ProcessGroup | None = None, data_bytes: int | None = None,
-                         arenas: dict[str, float] | None = None) -> SymmetricMemory:
-    """One shared region per process group (created on first use)."""
+                         arenas: dict[str, float] | None = None, tag: str = "") -> SymmetricMemory:
+    """One shared region per (process group, tag), created on first use. Users with their own sizing (the EP staging
+    buffers) pass a ``tag`` so that they do not land in a region another user sized for itself — PyTorch hands out the
+    same group object for equal rank sets, e.g. the FSDP shard group and the EP group of an all-EP job."""
     g = group if group is not None else dist.group.WORLD
-    key = id(g)
+    key = (id(g), tag)
     if key not in _default:
         if data_bytes is None:
             data_bytes = int(os.environ.get("VB200_SYMM_BYTES", str(1 << 30)))
