@@ -183,6 +183,9 @@ int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void* v, const 
                              const float* delta, void* dq, void* dk, void* dv, const int32_t* cu_seqlens,
                              int32_t num_seqs, int32_t max_seqlen, int32_t total, int32_t q_heads, int32_t k_heads,
                              int32_t head_dim, const int64_t* strides, float scale, int32_t causal, void* stream);
+/* Debugging aid (tools/attn_trace.py): with bit 13 of `causal` set, vb200_attn_varlen_bwd_tc records clock64 stamps of the
+ * hand-offs of block 0 of the dQ kernel; this copies them out (8 events x 64 tiles of int64).                         */
+int vb200_attn_debug_trace(int64_t* out512);
 int vb200_attn_varlen_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                           const float* lse, float* delta, void* dq, void* dk, void* dv,
                           const int32_t* cu_seqlens, int32_t num_seqs, int32_t max_seqlen, int32_t total,

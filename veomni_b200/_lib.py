@@ -58,6 +58,7 @@ SIGNATURES = {
     "vb200_attn_varlen_fwd_tc": (c_int, [_P] * 6 + [_I32] * 6 + [_P, _F, _I32, _P]),
     "vb200_attn_bwd_delta": (c_int, [_P, _P, _P, _I32, _I32, _I32, _I64, _I64, _I64, _I64, _P]),
     "vb200_attn_varlen_bwd_tc": (c_int, [_P] * 10 + [_I32] * 6 + [_P, _F, _I32, _P]),
+    "vb200_attn_debug_trace": (c_int, [_P]),
     "vb200_attn_varlen_bwd": (c_int, [_P] * 11 + [_I32] * 6 + [_P, _F, _I32, _P]),
     "vb200_moe_route_workspace": (_I64, [_I64, _I32]),
     "vb200_moe_route": (c_int, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _P]),

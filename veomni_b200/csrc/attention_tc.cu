@@ -328,7 +328,13 @@ struct AttnTcBwdParams {
     int64_t dq_st, dq_sh, dk_st, dk_sh, dv_st, dv_sh;
     const __nv_bfloat16 *q, *dout;  // raw pointers: the dQ kernel keeps its Q / dO tile in TMEM (A operands)
     int64_t q_st, q_sh, do_st, do_sh;
+    long long* trace;  // debugging: clock64 stamps of block 0's hand-offs ([event][tile], 64 tiles); nullptr in production
 };
+
+// Debug timeline of the dQ kernel (tools/attn_trace.py): events 0..5 of tile j < 64 in block 0.
+constexpr int kTraceTiles = 64;
+__device__ long long g_attn_trace[8 * kTraceTiles];
+#define VB_TRACE(ev, j) do { if (p.trace && blockIdx.x == 0 && (j) < kTraceTiles) p.trace[(ev) * kTraceTiles + (j)] = clock64(); } while (0)
 
 constexpr int TB_N = 64;                      // streamed tile rows
 constexpr int TB_SMALL = TB_N * TC_D * 2;     // 16 KB: a [64][128] bf16 tile (two 8 KB boxes)
@@ -432,6 +438,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 mbar_wait(&bar[Q_VFULL + ks], kph);
                 tc_fence_after();
                 if (elect_one_sync()) {
+                    VB_TRACE(0, j);  // S/dP of tile j issued
                     const uint32_t k_addr = smem_u32(sK + ks * TB_SMALL), v_addr = smem_u32(sV + ks * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TC_D / 16; ++k) {
@@ -464,6 +471,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 mbar_wait(&bar[Q_DSFULL + st], ph);
                 tc_fence_after();
                 if (elect_one_sync()) {
+                    VB_TRACE(1, i);  // dS of tile i seen by the MMA warp, dQ MMAs issued
                     const uint32_t ds_addr = smem_u32(sdS + st * TB_DS), k_addr = smem_u32(sK + ks * TB_SMALL);
 #pragma unroll
                     for (int k = 0; k < TB_N / 16; ++k)
@@ -519,7 +527,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const uint32_t ph = (uint32_t)(j >> 1) & 1u;
             mbar_wait(&bar[Q_SPFULL + st], ph);
             tc_fence_after();
+            if (warp == 2 && lane == 0) VB_TRACE(2, j);  // S/dP of tile j complete (seen by softmax warp 2)
             mbar_wait(&bar[Q_DSEMPTY + st], ph ^ 1);  // dS[st] free (dQ_{j-2} committed)
+            if (warp == 2 && lane == 0) VB_TRACE(3, j);
             const uint32_t ds_a = smem_u32(sdS + st * TB_DS);
             // tiles fully below the diagonal and inside the sequence need no per-element predicate
             const bool need_mask = (j * TB_N + TB_N > L) || (m0 + TC_BM > L) || (p.causal && j * TB_N + TB_N > m0);
@@ -529,6 +539,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tmem_ld32_nowait(lane_base + st * TB_N + c * 32, sv);
                 tmem_ld32_nowait(lane_base + 128 + st * TB_N + c * 32, dv);
                 tmem_wait_ld();
+                if (warp == 2 && lane == 0) VB_TRACE(4, j);  // S/dP chunk in registers
                 // S/dP[st] are in registers: release the TMEM buffer now so the MMA warp can run S/dP of tile j+2
                 // while this tile's exponentials are still being computed
                 if (!PP || c == 1) {
@@ -564,10 +575,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                                  "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
                 }
             }
+            if (warp == 2 && lane == 0) VB_TRACE(5, j);  // dS chunk stored
             tc_fence_before();
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar[Q_DSFULL + st]);
+            if (warp == 2 && lane == 0) VB_TRACE(6, j);  // arrived
         }
         mbar_wait(&bar[Q_DONE], 0);
         tc_fence_after();
@@ -987,6 +1000,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     const bool ss_operands = (causal >> 10) & 1;  // bit 10: all MMA operands from shared memory (cross-check variant)
     const bool pingpong = (causal >> 11) & 1;     // bit 11: softmax warpgroups on alternate tiles
     const bool p16 = (causal >> 12) & 1;          // bit 12: sixteen softmax warps, two groups of eight on alternate tiles
+    const bool trace = (causal >> 13) & 1;        // bit 13: debug timeline of block 0 of the dQ kernel (vb200_attn_debug_trace)
     causal &= 1;
     if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: head_dim must be 128");
     if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: Hq % Hk != 0");
@@ -1011,6 +1025,13 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     p.dv = (__nv_bfloat16*)dv; p.dv_st = st[12]; p.dv_sh = st[13];
     p.q = (const __nv_bfloat16*)q; p.q_st = st[0]; p.q_sh = st[1];
     p.dout = (const __nv_bfloat16*)dout; p.do_st = st[6]; p.do_sh = st[7];
+    p.trace = nullptr;
+    if (trace) {
+        void* sym = nullptr;
+        VB_CUDA_TRY(cudaGetSymbolAddress(&sym, g_attn_trace));
+        VB_CUDA_TRY(cudaMemsetAsync(sym, 0, sizeof(long long) * 8 * kTraceTiles, (cudaStream_t)stream));
+        p.trace = (long long*)sym;
+    }
     const size_t smem_dq = 2 * TC_TILE + 2 * TB_KV_SS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
     const size_t smem_dq_ts = 2 * TB_KV_TS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
     const size_t smem_kv = 2 * TC_TILE + 2 * TB_QS_SS * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
@@ -1048,5 +1069,13 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
         vb200_count_launch(1);
     }
     VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+// Debugging: copy the last dQ-kernel timeline (8 events x 64 tiles of clock64 stamps, block 0) to host memory.
+extern "C" int vb200_attn_debug_trace(int64_t* out512) {
+    if (!out512) return vb200_set_error(VB200_EINVAL, "attn_debug_trace: null output");
+    VB_CUDA_TRY(cudaDeviceSynchronize());
+    VB_CUDA_TRY(cudaMemcpyFromSymbol(out512, g_attn_trace, sizeof(long long) * 8 * kTraceTiles));
     return VB200_OK;
 }
