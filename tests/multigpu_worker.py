@@ -173,6 +173,53 @@ def test_fsdp(rank, world, dev):
         assert torch.equal(got[True][n], got[False][n]), f"bf16-packed reduce-scatter changed the gradient of {n}"
 
 
+def test_async_ulysses(rank, world, dev):
+    """Async-Ulysses q/k/v and output projections == the synchronous path (projection -> exchange -> q/k RMSNorm), the parity
+    target of the reference's own test (tests/parallel/ulysses/test_async_ulysses.py:112-115): outputs bit-exact (same kernels,
+    same order), gradients to GEMM-summation-order tolerance."""
+    from veomni_b200 import functional as F
+    from veomni_b200 import ulysses as U
+    from veomni_b200.async_ulysses import async_ulysses_output_projection, async_ulysses_qkv_projection
+
+    BF = torch.bfloat16
+    H, nq, nkv, D = 256, 4 * world, max(2, world), 64
+    Sl = 40 + 0  # local tokens per rank (same on every rank)
+    g = torch.Generator().manual_seed(900)  # same weights everywhere
+    qw = (0.05 * torch.randn(nq * D, H, generator=g)).to(BF).to(dev)
+    kw = (0.05 * torch.randn(nkv * D, H, generator=g)).to(BF).to(dev)
+    vw = (0.05 * torch.randn(nkv * D, H, generator=g)).to(BF).to(dev)
+    ow = (0.05 * torch.randn(H, nq * D, generator=g)).to(BF).to(dev)
+    nqw = (1 + 0.1 * torch.randn(D, generator=g)).to(BF).to(dev)
+    nkw = (1 + 0.1 * torch.randn(D, generator=g)).to(BF).to(dev)
+    g2 = torch.Generator().manual_seed(901 + rank)
+    hs = torch.randn(1, Sl, H, generator=g2).to(BF).to(dev)
+    res = {}
+    for mode in ("sync", "async"):
+        leaves = [t.clone().requires_grad_(True) for t in (hs, qw, kw, vw, ow, nqw, nkw)]
+        h, a, b, c, o, n1, n2 = leaves
+        if mode == "async":
+            q, k, v = async_ulysses_qkv_projection(h, 1, 2, a, None, b, None, c, None, "rmsnorm", n1, None, n2, None, D, 1e-6,
+                                                   Sl * world, D)
+        else:
+            q = U.gather_seq_scatter_heads(torch.nn.functional.linear(h, a).view(1, -1, nq, D), seq_dim=1, head_dim=2)
+            k = U.gather_seq_scatter_heads(torch.nn.functional.linear(h, b).view(1, -1, nkv, D), seq_dim=1, head_dim=2)
+            v = U.gather_seq_scatter_heads(torch.nn.functional.linear(h, c).view(1, -1, nkv, D), seq_dim=1, head_dim=2)
+            q, k = F.rms_norm(q, n1, 1e-6), F.rms_norm(k, n2, 1e-6)
+        att = q * 0.5 + k.repeat_interleave(nq // nkv, dim=2) * 0.25 + v.repeat_interleave(nq // nkv, dim=2)  # stand-in for attention
+        if mode == "async":
+            out = async_ulysses_output_projection(att, 1, 2, o, None, att.shape[1])
+        else:
+            out = torch.nn.functional.linear(U.gather_heads_scatter_seq(att, head_dim=2, seq_dim=1).reshape(1, Sl, -1), o)
+        out.float().square().mean().backward()
+        torch.cuda.synchronize()
+        res[mode] = ([q.detach(), k.detach(), v.detach(), out.detach()], [t.grad for t in leaves])
+    for x, y in zip(res["sync"][0], res["async"][0]):
+        assert torch.equal(x, y), "async-Ulysses forward differs from the synchronous path"
+    for i, (x, y) in enumerate(zip(res["sync"][1], res["async"][1])):
+        sc = max(1e-6, float(x.float().abs().max()))
+        torch.testing.assert_close(y.float() / sc, x.float() / sc, atol=2e-2, rtol=2e-2, msg=lambda m, i=i: f"async-Ulysses grad {i}: {m}")
+
+
 def test_ulysses_model(rank, world, dev):
     """Toy Qwen3 through the host caller with Ulysses SP over all ranks vs the reference fixture (loss, grad-norm)."""
     from veomni_b200.host_qwen3 import Qwen3Config, Qwen3ForCausalLM
@@ -464,6 +511,7 @@ def main():
     stage("reduce-scatter with fused copy-in (generic instantiation)", selfcheck.check_reduce_scatter_push, symm, dev)
     os.environ.pop("VB200_RS_GENERIC")
     stage("ulysses", test_ulysses, rank, world, dev)
+    stage("async ulysses projections == synchronous path", test_async_ulysses, rank, world, dev)
     stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
     stage("fsdp2 custom comm: every mode, ragged shapes, divide factor (self-check)", selfcheck.check_fsdp, dev, world)
     stage("EP dispatch/combine (self-check)", selfcheck.check_ep_dispatch, symm, dev)

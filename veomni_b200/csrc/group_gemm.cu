@@ -21,6 +21,8 @@
 // synchronisation is needed (the reference launches a max_M-sized grid and early-exits, :97-98).
 // Ragged edges: M tails are handled by row guards at the store; the ragged-K tail of mode TN is zeroed in
 // shared memory (A operand rows past the group's end) before the MMA consumes the stage.
+#include <cstdlib>
+
 #include "umma.cuh"
 
 namespace vb {
@@ -28,7 +30,8 @@ namespace vb {
 constexpr int GG_BM = 128, GG_BN = 256, GG_BK = 64, GG_STAGES = 4;
 constexpr int GG_STAGE_BYTES = (GG_BM + GG_BN) * GG_BK * 2;  // 48 KB (a 128x256 tile halves the L2->smem bytes per FLOP of 128x128)
 constexpr int GG_MAX_G = 1024;
-constexpr int GG_THREADS = 192;
+constexpr int GG_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
+constexpr int GG_EPI_WARPS = 8;
 
 enum { GG_NT = 0, GG_NN = 1, GG_TN = 2 };
 
@@ -107,7 +110,7 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tile_start[p.G] = run;
         for (int s = 0; s < GG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], GG_EPI_WARPS); }
         mbar_fence_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -200,8 +203,11 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++acc == 2) { acc = 0; aph ^= 1; }
         }
     } else {
-        // ===== epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =====
+        // ===== epilogue (warps 2..9; TMEM lane quadrant = warp % 4; warps w and w+4 split the tile's columns) =====
+        // With short reductions (wgrad: K_g ~ 256 tokens = 4 k-blocks, ~2000 clk of MMA per tile) the epilogue of a
+        // 128x256 tile is longer than its mainloop; eight warps halve it.
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         int acc = 0;
         uint32_t aph = 0;
         TileInfo ti;
@@ -222,7 +228,7 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             const int ncols = min(GG_BN, p.N - ti.nt * GG_BN);
 #pragma unroll 1
-            for (int c = 0; c < GG_BN / 32; ++c) {
+            for (int c = half * (GG_BN / 64); c < (half + 1) * (GG_BN / 64); ++c) {
                 uint32_t v[32];
                 if (kblocks > 0) {
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GG_BN + c * 32, v);
@@ -261,6 +267,186 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+
+// ================================================================================================================
+// Swapped-operand variant for the ragged-M modes (NT forward, NN dgrad):  C^T tile = W tile (M side) x tokens^T (N side).
+//   D[128 weight rows (output features), ntok tokens] = W_g[128, K] * X[rows of group g, K]^T
+// Why: the tensor core's M is 128 rows or nothing, its N is any multiple of 16 up to 256. With tokens on M (the layout of
+// group_gemm_kernel above, and of the reference's Triton kernel) an expert with 260 tokens costs three 128-row tiles
+// (+48 % padding work; Qwen3-30B-A3B at T=4096 averages 256 tokens per expert: ~25 % of all MMA work is padding);
+// with tokens on N the same expert is one 256-token tile plus one 16-token tile (N = 16), and every weight tile is
+// streamed from HBM/L2 once per <= 256 tokens instead of once per 128.
+// Output features sit on TMEM lanes, tokens on columns: the epilogue stores C[token][feature] with the 32 lanes of a
+// warp on 32 consecutive features (64-byte segments).
+// ================================================================================================================
+constexpr int GS_BM = 128;   // weight rows (output features) per tile
+constexpr int GS_TOK = 256;  // tokens per tile (MMA N <= 256)
+constexpr int GS_STAGE_BYTES = (GS_BM + GS_TOK) * GG_BK * 2;  // 48 KB
+
+struct SwapTile {
+    int g, tt, wt;
+    int row0;        // first token row of the tile
+    int rows_valid;  // 1..256 tokens of the group in this tile
+    int ntok;        // MMA N: rows_valid rounded up to 16
+};
+
+__device__ __forceinline__ bool get_swap_tile(int t, const int* tile_start, const GGParams& p, int n_wt, SwapTile& ti) {
+    if (t >= tile_start[p.G]) return false;
+    int lo = 0, hi = p.G - 1;  // tile_start[lo] <= t < tile_start[lo + 1]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tile_start[mid + 1] <= t) lo = mid + 1;
+        else hi = mid;
+    }
+    ti.g = lo;
+    const int r = t - tile_start[lo];
+    ti.tt = r / n_wt;
+    ti.wt = r - ti.tt * n_wt;  // weight tile fastest: CTAs working on consecutive t share the token tile in L2
+    const int s = lo ? p.cumsum[lo - 1] : 0;
+    ti.row0 = s + ti.tt * GS_TOK;
+    ti.rows_valid = min(GS_TOK, p.cumsum[lo] - ti.row0);
+    ti.ntok = (ti.rows_valid + 15) & ~15;
+    return true;
+}
+
+// NN = false: W is [G, N, K] (transpose_b=True, forward);  NN = true: W is [G, K, N] (dgrad)
+template <bool NN>
+__global__ void __launch_bounds__(GG_THREADS, 1)
+group_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const GGParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* stages = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GG_STAGES * GS_STAGE_BYTES);
+    uint64_t* empty = full + GG_STAGES;
+    uint64_t* tfull = empty + GG_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    int* tile_start = reinterpret_cast<int*>(tmem_slot + 2);  // [G+1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_wt = (p.N + GS_BM - 1) / GS_BM;
+    const int kblocks = (p.K + GG_BK - 1) / GG_BK;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int g = 0; g < p.G; ++g) {
+            tile_start[g] = run;
+            const int rows = p.cumsum[g] - (g ? p.cumsum[g - 1] : 0);
+            run += ((rows + GS_TOK - 1) / GS_TOK) * n_wt;
+        }
+        tile_start[p.G] = run;
+        for (int s = 0; s < GG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], GG_EPI_WARPS); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * GS_TOK);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one_sync()) {
+            int s = 0;
+            uint32_t ph = 0;
+            SwapTile ti;
+            for (int t = blockIdx.x; get_swap_tile(t, tile_start, p, n_wt, ti); t += gridDim.x) {
+                const int nbox = (ti.ntok + 63) >> 6;  // 64-token boxes actually needed
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* sa = stages + s * GS_STAGE_BYTES;  // weight tile [128 features x 64 k]
+                    uint8_t* sb = sa + GS_BM * GG_BK * 2;       // token tile  [<=256 tokens x 64 k]
+                    mbar_expect_tx(&full[s], GS_BM * GG_BK * 2 + nbox * 64 * GG_BK * 2);
+                    if (!NN) {
+                        tma_load_3d(sa, &tmW, kb * GG_BK, ti.wt * GS_BM, ti.g, &full[s]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < GS_BM / 64; ++i)
+                            tma_load_3d(sa + i * GG_BK * 128, &tmW, ti.wt * GS_BM + i * 64, kb * GG_BK, ti.g, &full[s]);
+                    }
+                    for (int i = 0; i < nbox; ++i)
+                        tma_load_2d(sb + i * 64 * 128, &tmX, kb * GG_BK, ti.row0 + i * 64, &full[s]);
+                    if (++s == GG_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        int s = 0, acc = 0;
+        uint32_t ph = 0, aph = 0;
+        SwapTile ti;
+        for (int t = blockIdx.x; get_swap_tile(t, tile_start, p, n_wt, ti); t += gridDim.x) {
+            const uint32_t idesc = umma_idesc(NN ? 1 : 0, 0, GS_BM, ti.ntok);
+            mbar_wait(&tempty[acc], aph ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * GS_TOK;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                uint8_t* sa = stages + s * GS_STAGE_BYTES;
+                uint8_t* sb = sa + GS_BM * GG_BK * 2;
+                if (elect_one_sync()) {
+                    const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
+#pragma unroll
+                    for (int k = 0; k < GG_BK / 16; ++k) {
+                        // A = weights: K-major (forward) or MN-major (dgrad, two 64-feature boxes); B = tokens, K-major
+                        const uint32_t a_off = NN ? k * 16 * 128 : k * 32, a_lbo = NN ? GG_BK * 128 : 16;
+                        umma_f16_bo(tmem_d, a_addr >> 4, a_off, a_lbo, 1024, b_addr >> 4, k * 32, 16, 1024, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++s == GG_STAGES) { s = 0; ph ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
+    } else {
+        // ===== epilogue (warps 2..9; TMEM lane quadrant = warp % 4): lane = output feature, column = token; warps w and
+        // w+4 take alternate 32-token chunks =====
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int acc = 0;
+        uint32_t aph = 0;
+        SwapTile ti;
+        for (int t = blockIdx.x; get_swap_tile(t, tile_start, p, n_wt, ti); t += gridDim.x) {
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const int f = ti.wt * GS_BM + q * 32 + lane;
+            const bool f_ok = f < p.N;
+            __nv_bfloat16* cbase = p.C + (int64_t)ti.row0 * p.N + f;
+            const int nch = (ti.rows_valid + 31) >> 5;
+#pragma unroll 1
+            for (int c = half; c < nch; c += 2) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GS_TOK + c * 32, v);
+                if (f_ok) {
+                    const int left = ti.rows_valid - c * 32;
+                    __nv_bfloat16* cp = cbase + (int64_t)c * 32 * p.N;
+                    if (left >= 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cp[(int64_t)j * p.N] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < left) cp[(int64_t)j * p.N] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * GS_TOK);
+    }
+}
+
 static size_t gg_smem_bytes(int G) {
     return (size_t)GG_STAGES * GG_STAGE_BYTES + (2 * GG_STAGES + 4) * 8 + 16 + (size_t)(G + 1) * 4 + 64;
 }
@@ -272,6 +458,8 @@ using namespace vb;
 // a: NT/NN [sumM, K]; TN [sumK, M].   b: NT [G, N, K]; NN [G, K, N]; TN [sumK, N].   c: NT/NN [sumM, N]; TN [G, M, N].
 extern "C" int vb200_group_gemm(int32_t mode, const void* a, const void* b, void* c, const int32_t* cumsum,
                                 int32_t num_groups, int64_t total_rows, int32_t m, int32_t n, int32_t k, void* stream) {
+    const int variant = (mode >> 8) & 3;  // bits 8-9: 0 = default, 1 = tokens on the MMA M side (classic), 2 = tokens on N (swapped)
+    mode &= 0xff;
     if (mode < 0 || mode > 2) return vb200_set_error(VB200_EINVAL, "group_gemm: mode must be 0 (NT), 1 (NN) or 2 (TN)");
     if (num_groups < 1 || num_groups > GG_MAX_G) return vb200_set_error(VB200_EINVAL, "group_gemm: 1..1024 groups");
     if (n <= 0 || (n & 7)) return vb200_set_error(VB200_EINVAL, "group_gemm: N must be a positive multiple of 8");
@@ -285,6 +473,30 @@ extern "C" int vb200_group_gemm(int32_t mode, const void* a, const void* b, void
     p.cumsum = cumsum; p.G = num_groups; p.M = m; p.N = n; p.K = k; p.C = (__nv_bfloat16*)c;
     const uint64_t rows = (uint64_t)(total_rows > 0 ? total_rows : 1);
     const size_t smem = gg_smem_bytes(num_groups);
+    static int swap_mode = -1;
+    if (swap_mode < 0) {
+        const char* e = getenv("VB200_GG_SWAP");
+        swap_mode = (e && e[0] == '1') ? 1 : 0;  // default off until validated on hardware
+    }
+    if (mode != GG_TN && (variant == 2 || (variant == 0 && swap_mode))) {
+        // tokens on the MMA N side (see group_gemm_swap_kernel)
+        const size_t smem_sw = (size_t)GG_STAGES * GS_STAGE_BYTES + (2 * GG_STAGES + 4) * 8 + 16 + (size_t)(num_groups + 1) * 4 + 64;
+        if ((rc = make_tmap_2d(&tmA, a, k, rows, k, 64))) return rc;  // tokens [rows, K], box 64 x 64
+        if (mode == GG_NT) {
+            if ((rc = make_tmap_3d_box(&tmB, b, k, n, num_groups, k, (uint64_t)n * k, 64, GS_BM))) return rc;
+            static bool attr = false;
+            if (!attr) { VB_CUDA_TRY(cudaFuncSetAttribute(group_gemm_swap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+            group_gemm_swap_kernel<false><<<kNumSMs, GG_THREADS, smem_sw, st>>>(tmA, tmB, p);
+        } else {
+            if ((rc = make_tmap_3d_box(&tmB, b, n, k, num_groups, n, (uint64_t)n * k, 64, GG_BK))) return rc;
+            static bool attr = false;
+            if (!attr) { VB_CUDA_TRY(cudaFuncSetAttribute(group_gemm_swap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+            group_gemm_swap_kernel<true><<<kNumSMs, GG_THREADS, smem_sw, st>>>(tmA, tmB, p);
+        }
+        vb200_count_launch(1);
+        VB_HOST_CHECK_LAUNCH();
+        return VB200_OK;
+    }
     if (mode == GG_NT) {
         if ((rc = make_tmap_2d(&tmA, a, k, rows, k, GG_BM))) return rc;
         if ((rc = make_tmap_3d_box(&tmB, b, k, n, num_groups, k, (uint64_t)n * k, 64, GG_BN))) return rc;

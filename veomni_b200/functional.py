@@ -322,3 +322,13 @@ def silu_mul(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
 def swiglu_mlp(module, x: torch.Tensor) -> torch.Tensor:
     """Drop-in for the ``swiglu_mlp`` OpSlot (veomni/ops/liger/__init__.py:127-130)."""
     return module.down_proj(silu_mul(module.gate_proj(x), module.up_proj(x)))
+
+
+def swiglu_mlp_residual(module, x: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+    """``residual + swiglu_mlp(module, x)`` with the residual add folded into the down-projection GEMM's epilogue
+    (cuBLAS beta = 1) instead of a separate elementwise kernel (patched_modeling_qwen3_gpu.py:375)."""
+    act = silu_mul(module.gate_proj(x), module.up_proj(x))
+    if module.down_proj.bias is not None:
+        return residual + module.down_proj(act)
+    shape = residual.shape
+    return torch.addmm(residual.reshape(-1, shape[-1]), act.reshape(-1, act.shape[-1]), module.down_proj.weight.t()).view(shape)

@@ -158,7 +158,7 @@ class Qwen3DecoderLayer(nn.Module):
         if self.fuse_add_norm:  # residual add fused into the post-attention RMSNorm
             n = self.post_attention_layernorm
             x, h = F.fused_add_rms_norm(a, h, n.weight, n.variance_epsilon)
-            return h + self.mlp(x)
+            return F.swiglu_mlp_residual(self.mlp, x, h)  # second residual add inside the down-projection GEMM
         h = h + a
         return h + self.mlp(self.post_attention_layernorm(h))
 

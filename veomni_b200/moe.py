@@ -114,9 +114,14 @@ def _cumsum32(c: torch.Tensor) -> torch.Tensor:
     return c if c.dtype == torch.int32 else c.to(torch.int32)
 
 
+# 0: library default (tokens on the MMA N side for the ragged-M modes); 1: classic (tokens on M); 2: swapped. Tests compare them.
+GG_VARIANT = 0
+
+
 def _gg(mode: int, a, b, c, cumsum, G, rows, m, n, k):
     lib = _lib.load()
-    flops = 2.0 * rows * (m * n if mode == 2 else n * k)
+    mode = mode | (GG_VARIANT << 8)
+    flops = 2.0 * rows * (m * n if (mode & 0xff) == 2 else n * k)
     with torch.cuda.device(a.device), prof.span("group_gemm", flops):
         check(lib.vb200_group_gemm(mode, a.data_ptr(), b.data_ptr(), c.data_ptr(), cumsum.data_ptr(), G, rows, m, n, k,
                                    stream_ptr()), "vb200_group_gemm")

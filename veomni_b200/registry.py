@@ -213,6 +213,10 @@ def register(force: bool = True) -> bool:
     from . import ulysses
 
     ulysses.install()
+    # async Ulysses (Qwen3-VL / Wan attention front and back end, sequence_parallel/async_ulysses.py:469-503)
+    from . import async_ulysses
+
+    async_ulysses.install()
     # fused MoE raw pointer (veomni/ops/kernels/moe/__init__.py:62-108)
     try:
         import veomni.ops.kernels.moe as ref_moe
