@@ -17,8 +17,12 @@
 
 namespace vb {
 
-constexpr int kHeadChunk = 8;  // heads per work item (cos/sin reuse)
-constexpr int kSub = 4;        // heads in flight per thread (register budget: 2 CTAs/SM)
+// Work item = (token, kHeadChunk heads). These are 15-40 us kernels on 296 resident CTAs: with 8-head items the T=4096,
+// 40-head problem is 2.16 items per lane group, i.e. a third pass that is 16 % full (72 % of the achievable rate; the
+// backward's capped grid did worse); 2-head items make it 8.65 -> 9 passes (96 %). cos/sin rows are re-read per item,
+// from L2 (1 MB in total).
+constexpr int kHeadChunk = 2;  // heads per work item
+constexpr int kSub = 2;        // heads in flight per thread (all of an item: 8 x 16 B loads + the 4 table loads)
 
 struct RopeTables {
     float c_lo[8], c_hi[8], s_lo[8], s_hi[8];
@@ -216,28 +220,47 @@ qknorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq_out, const __nv_bflo
         const bool item_ok = item < items;
         const int64_t tok = item_ok ? item / nchunks : 0;
         const int h0 = item_ok ? (int)(item % nchunks) * kHeadChunk : 0;
-        RopeTables t;
-        load_tables(t, cos, sin, tok, D, sub);
-#pragma unroll 1
+        // cos/sin stay packed (bf16x8) until used: the unpacked tables would cost 32 registers next to the 32 dw accumulators
+        const uint4 tcl = *reinterpret_cast<const uint4*>(cos + tok * D + sub * 8), tch = *reinterpret_cast<const uint4*>(cos + tok * D + HALF + sub * 8);
+        const uint4 tsl = *reinterpret_cast<const uint4*>(sin + tok * D + sub * 8), tsh = *reinterpret_cast<const uint4*>(sin + tok * D + HALF + sub * 8);
+        // all loads of the item first (8 x 16 B in flight per thread), then the arithmetic
+        uint4 gv[kHeadChunk][2], xv[kHeadChunk][2];
+        float rsv[kHeadChunk];
+#pragma unroll
+        for (int j = 0; j < kHeadChunk; ++j) {
+            const int h = h0 + j;
+            const bool is_q = h < Hq;
+            const int64_t row = is_q ? (tok * Hq + h) : (tok * Hk + (h - Hq));
+            gv[j][0] = gv[j][1] = xv[j][0] = xv[j][1] = make_uint4(0, 0, 0, 0);
+            rsv[j] = 0.f;
+            if (item_ok && h < H) {
+                const __nv_bfloat16* gsrc = (is_q ? dq_out : dk_out) + row * D;
+                const __nv_bfloat16* xsrc = (is_q ? q_in : k_in) + row * D;
+                gv[j][0] = ldg_stream(gsrc + sub * 8);
+                gv[j][1] = ldg_stream(gsrc + HALF + sub * 8);
+                xv[j][0] = ldg_stream(xsrc + sub * 8);
+                xv[j][1] = ldg_stream(xsrc + HALF + sub * 8);
+                rsv[j] = is_q ? rstd_q[row] : rstd_k[row];
+            }
+        }
+#pragma unroll
         for (int j = 0; j < kHeadChunk; ++j) {
             const int h = h0 + j;
             const bool ok = item_ok && h < H;
             const bool is_q = h < Hq;
             const int64_t row = is_q ? (tok * Hq + h) : (tok * Hk + (h - Hq));
-            float glo[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ghi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            float xlo[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xhi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            float rs = 0.f;
-            if (ok) {
-                const __nv_bfloat16* gsrc = (is_q ? dq_out : dk_out) + row * D;
-                const __nv_bfloat16* xsrc = (is_q ? q_in : k_in) + row * D;
-                unpack8(ldg_stream(gsrc + sub * 8), glo);
-                unpack8(ldg_stream(gsrc + HALF + sub * 8), ghi);
-                unpack8(ldg_stream(xsrc + sub * 8), xlo);
-                unpack8(ldg_stream(xsrc + HALF + sub * 8), xhi);
-                rs = is_q ? rstd_q[row] : rstd_k[row];
-            }
+            float glo[8], ghi[8], xlo[8], xhi[8];
+            unpack8(gv[j][0], glo);
+            unpack8(gv[j][1], ghi);
+            unpack8(xv[j][0], xlo);
+            unpack8(xv[j][1], xhi);
+            const float rs = rsv[j];
             float dlo[8], dhi[8];
-            rotate_bwd(t, glo, ghi, dlo, dhi);  // dy of the norm
+            {
+                RopeTables t;
+                unpack8(tcl, t.c_lo); unpack8(tch, t.c_hi); unpack8(tsl, t.s_lo); unpack8(tsh, t.s_hi);
+                rotate_bwd(t, glo, ghi, dlo, dhi);  // dy of the norm
+            }
             float dot = 0.f, w_lo[8], w_hi[8];
             unpack8(is_q ? wq_lo_p : wk_lo_p, w_lo);
             unpack8(is_q ? wq_hi_p : wk_hi_p, w_hi);
@@ -333,7 +356,7 @@ extern "C" int vb200_rope(const void* q_in, void* q_out, const void* k_in, void*
     if (tokens <= 0 || q_heads + k_heads <= 0) return VB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int lph = head_dim / 16;
-    const int g = items_grid(tokens, q_heads + k_heads, lph, 8 * kNumSMs);
+    const int g = items_grid(tokens, q_heads + k_heads, lph, 2 * kNumSMs);
 #define GO(L)                                                                                            \
     rope_kernel<L><<<g, 256, 0, st>>>((const __nv_bfloat16*)q_in, (__nv_bfloat16*)q_out,                 \
                                       (const __nv_bfloat16*)k_in, (__nv_bfloat16*)k_out,                 \
@@ -358,7 +381,7 @@ extern "C" int vb200_qknorm_rope_fwd(const void* q_in, const void* k_in, const v
     if (tokens <= 0) return VB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int lph = head_dim / 16;
-    const int g = items_grid(tokens, q_heads + k_heads, lph, 8 * kNumSMs);
+    const int g = items_grid(tokens, q_heads + k_heads, lph, 2 * kNumSMs);  // = the resident CTAs (launch bounds 256 x 2)
 #define GO(L)                                                                                           \
     qknorm_rope_fwd_kernel<L><<<g, 256, 0, st>>>(                                                       \
         (const __nv_bfloat16*)q_in, (const __nv_bfloat16*)k_in, (const __nv_bfloat16*)wq,               \
@@ -393,7 +416,7 @@ extern "C" int vb200_qknorm_rope_bwd(const void* dq_out, const void* dk_out, con
         return VB200_OK;
     }
     const int lph = head_dim / 16;
-    const int g = items_grid(tokens, q_heads + k_heads, lph, 4 * kNumSMs);
+    const int g = items_grid(tokens, q_heads + k_heads, lph, 2 * kNumSMs);  // = the resident CTAs
 #define GO(L)                                                                                           \
     qknorm_rope_bwd_kernel<L><<<g, 256, 0, st>>>(                                                       \
         (const __nv_bfloat16*)dq_out, (const __nv_bfloat16*)dk_out, (const __nv_bfloat16*)q_in,         \
