@@ -217,7 +217,7 @@ def test_attention_tcgen05_operand_variants_agree(cuda_dev):
     and at the Qwen3-8B size."""
     from veomni_b200 import attention as A
 
-    old = (A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS, A.BWD_PP, A.BWD_P16)
+    old = (A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS, A.BWD_PP, A.BWD_P16, A.BWD_DQ_N128)
     try:
         A.FWD_IMPL = A.BWD_IMPL = "tc"
         for lens, Hq, Hk in (([1, 63, 64, 65, 127, 129, 300], 4, 2), ([700, 64], 6, 1), ([4096], 32, 8)):
@@ -226,16 +226,17 @@ def test_attention_tcgen05_operand_variants_agree(cuda_dev):
             q, k, v, do = (torch.randn(T, h, 128, generator=g).to(BF).to(cuda_dev) for h in (Hq, Hk, Hk, Hq))
             cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
             grads = {}
-            for variant in ("tmem", "smem", "pingpong", "p16"):
+            for variant in ("tmem", "smem", "pingpong", "p16", "dq_n128"):
                 A.BWD_DQ_SS, A.BWD_PP, A.BWD_P16 = variant == "smem", variant == "pingpong", variant == "p16"
+                A.BWD_DQ_N128 = variant == "dq_n128"
                 qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
                 A.flash_attn_varlen(qq, kk, vv, cu, max(lens)).backward(do)
                 grads[variant] = (qq.grad, kk.grad, vv.grad)
-            for variant in ("smem", "pingpong", "p16"):
+            for variant in ("smem", "pingpong", "p16", "dq_n128"):
                 for a, b in zip(grads["tmem"], grads[variant]):
                     assert torch.equal(a, b), (variant, lens)
     finally:
-        A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS, A.BWD_PP, A.BWD_P16 = old
+        A.FWD_IMPL, A.BWD_IMPL, A.BWD_DQ_SS, A.BWD_PP, A.BWD_P16, A.BWD_DQ_N128 = old
 
 
 def test_attention_tcgen05_forward_eight_softmax_warps(cuda_dev):

@@ -77,6 +77,21 @@ def bench_attention(dev, iters):
         except Exception as ex:  # noqa: BLE001
             print({"attn_bwd_p16": str(ex)})
     A.BWD_P16 = False
+    for n128 in (False, True):
+        A.BWD_DQ_N128 = n128
+        try:
+            qg, kg, vg = gsets[0]
+            o = flash_attn_varlen(qg, kg, vg, cu, T)
+
+            def bwd_only2():
+                o.backward(do, retain_graph=True)
+                qg.grad = kg.grad = vg.grad = None
+
+            report(f"attn_bwd only (delta + dQ + dK/dV) (DQ_N128={n128})[4096,32/8,128,causal]", time_fn(lambda: bwd_only2(), [()], iters),
+                   flops=flops_fwd * 2.5)
+        except Exception as ex:  # noqa: BLE001
+            print({"attn_bwd_dq_n128": str(ex)})
+    A.BWD_DQ_N128 = False
     A.FWD_IMPL, A.BWD_IMPL = old2
     try:
         from flash_attn import flash_attn_varlen_func

@@ -611,6 +611,233 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
 }
 
+// ================================================================================================================
+// dQ kernel with 128-row K/V tiles ("N128").
+// Timeline of the 64-row kernel above (tools/attn_trace.py, profiles/r02_attn_trace.txt): 1528 clk per 128x64 tile in
+// steady state against ~770 clk of tensor-core math — the 20 small MMAs per tile (16 with N = 64) plus five commits keep
+// the MMA stream itself at ~1140 clk (tools/ubench_sm100.cu), and doubling the softmax warps (P16) changed nothing: the
+// stage is bound by the MMA stream, not by the exponentials. This variant halves the instruction count per FLOP:
+//   S = Q K^T and dP = dO V^T as 8 + 8 MMAs with N = 128 into SINGLE TMEM buffers (S cols 0..127, dP 128..255): the
+//       sixteen softmax warps (four per TMEM lane quadrant, 32 columns each) pull a tile into registers right after its
+//       commit and release the buffers at once, so the next tile's S/dP run while this tile's exponentials are computed;
+//   dQ += dS K as 8 MMAs (K = 128) from ONE 32 KB dS buffer (the wait for its previous reader sits right before the
+//       stores, i.e. after the exponentials);
+//   K/V ring: 3 stages of 2 x 32 KB. One diagonal (masked) tile per CTA instead of two.
+// Same arithmetic in the same order as the 64-row kernel (the TMEM accumulator sees the same k-steps): bit-identical dQ.
+// ================================================================================================================
+constexpr int N8_BN = 128, N8_KV = 3;
+constexpr int N8_TILE = N8_BN * TC_D * 2;  // 32 KB: a [128][128] bf16 tile (two [128][64] boxes)
+enum { N8_LOAD = 0, N8_KFULL = 1, N8_VFULL = N8_KFULL + N8_KV, N8_KEMPTY = N8_VFULL + N8_KV, N8_VEMPTY = N8_KEMPTY + N8_KV,
+       N8_SPFULL = N8_VEMPTY + N8_KV, N8_SEMPTY, N8_DSFULL, N8_DSEMPTY, N8_DONE, N8_COUNT };
+
+__global__ void __launch_bounds__(576, 1)
+attn_bwd_dq_n128_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnTcBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sK = smem;                      // N8_KV x 32 KB
+    uint8_t* sV = sK + N8_KV * N8_TILE;      // N8_KV x 32 KB
+    uint8_t* sdS = sV + N8_KV * N8_TILE;     // 32 KB
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sdS + N8_TILE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + N8_COUNT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int order, h, seq;
+    tile_of_block(p.Hq, p.nseq, order, h, seq);
+    const int s0 = p.cu_seqlens[seq], L = p.cu_seqlens[seq + 1] - s0;
+    const int mblk = p.tiles - 1 - order;  // causal: the last Q tile is the heaviest
+    const int m0 = mblk * TC_BM;
+    if (m0 >= L) return;
+    const int hk = h / (p.Hq / p.Hk);
+    const int kv_end = p.causal ? min(L, m0 + TC_BM) : L;
+    const int n_tiles = (kv_end + N8_BN - 1) / N8_BN;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < N8_COUNT; ++i) {
+            const int cnt = (i == N8_SEMPTY || i == N8_DSFULL) ? 16 : (i == N8_LOAD ? 8 : 1);
+            mbar_init(&bar[i], cnt);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // TMEM columns: S 0..127, dP 128..255, dQ 256..383, Q (bf16 A operand) 384..447, dO 448..511
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j % N8_KV;
+                const uint32_t ph = (uint32_t)(j / N8_KV) & 1u;
+                mbar_wait(&bar[N8_KEMPTY + st], ph ^ 1);
+                mbar_expect_tx(&bar[N8_KFULL + st], N8_TILE);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_3d(sK + st * N8_TILE + hf * N8_BN * 128, &tmK, hf * 64, hk, s0 + j * N8_BN, &bar[N8_KFULL + st]);
+                mbar_wait(&bar[N8_VEMPTY + st], ph ^ 1);
+                mbar_expect_tx(&bar[N8_VFULL + st], N8_TILE);
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_3d(sV + st * N8_TILE + hf * N8_BN * 128, &tmV, hf * 64, hk, s0 + j * N8_BN, &bar[N8_VFULL + st]);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_nt = umma_idesc(0, 0, TC_BM, N8_BN);  // S, dP: N = 128, both operands K-major
+        constexpr uint32_t idesc_dq = umma_idesc(0, 1, TC_BM, TC_D);   // dQ: A = dS (K-major), B = K (MN-major)
+        mbar_wait(&bar[N8_LOAD], 0);
+        for (int j = 0; j <= n_tiles; ++j) {
+            if (j < n_tiles) {
+                const uint32_t ph = (uint32_t)j & 1u;
+                const int ks = j % N8_KV;
+                const uint32_t kph = (uint32_t)(j / N8_KV) & 1u;
+                mbar_wait(&bar[N8_SEMPTY], ph ^ 1);  // tile j-1's S/dP are in the softmax warps' registers
+                mbar_wait(&bar[N8_KFULL + ks], kph);
+                mbar_wait(&bar[N8_VFULL + ks], kph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t k_addr = smem_u32(sK + ks * N8_TILE), v_addr = smem_u32(sV + ks * N8_TILE);
+#pragma unroll
+                    for (int k = 0; k < TC_D / 16; ++k) {  // A = Q rows in TMEM: 16 bf16 of K per step = 8 columns
+                        const uint32_t b_off = (uint32_t)(k >> 2) * (N8_BN * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16_ts(tmem, tmem + 384 + k * 8, k_addr >> 4, b_off, 16, 1024, idesc_nt, k ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < TC_D / 16; ++k) {
+                        const uint32_t b_off = (uint32_t)(k >> 2) * (N8_BN * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16_ts(tmem + 128, tmem + 448 + k * 8, v_addr >> 4, b_off, 16, 1024, idesc_nt, k ? 1u : 0u);
+                    }
+                    umma_commit(&bar[N8_VEMPTY + ks]);
+                    umma_commit(&bar[N8_SPFULL]);
+                }
+                __syncwarp();
+            }
+            if (j >= 1) {
+                const int i = j - 1, ks = i % N8_KV;
+                mbar_wait(&bar[N8_DSFULL], (uint32_t)i & 1u);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t ds_addr = smem_u32(sdS), k_addr = smem_u32(sK + ks * N8_TILE);
+#pragma unroll
+                    for (int k = 0; k < N8_BN / 16; ++k) {
+                        // A = dS [128 q][128 kv], K-major, two [128][64] halves; B = K tile [128 kv][128 d] read MN-major:
+                        // k-step k = kv rows 16k.., the two 64-wide d halves N8_BN*128 bytes apart
+                        const uint32_t a_off = (uint32_t)(k >> 2) * (TC_BM * 128) + (uint32_t)(k & 3) * 32;
+                        umma_f16_bo(tmem + 256, ds_addr >> 4, a_off, 16, 1024, k_addr >> 4, k * 16 * 128, N8_BN * 128, 1024, idesc_dq,
+                                    (i | k) ? 1u : 0u);
+                    }
+                    umma_commit(&bar[N8_KEMPTY + ks]);
+                    umma_commit(&bar[N8_DSEMPTY]);
+                    if (i == n_tiles - 1) umma_commit(&bar[N8_DONE]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // 16 softmax warps: four per TMEM lane quadrant (warp & 3), one 32-column chunk of the 128-column tile each
+        const int q = warp & 3;
+        const int cw = (warp - 2) >> 2;  // 0..3
+        const int r = q * 32 + lane;
+        const int m = m0 + r;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        const float sl2 = p.scale * kLog2eTc;
+        float lse2 = 0.f, dl = 0.f;
+        if (m < L) {
+            const float l = p.lse[(int64_t)h * p.total + s0 + m];
+            lse2 = (l == -INFINITY) ? 0.f : l * kLog2eTc;
+            dl = p.delta[(int64_t)h * p.total + s0 + m];
+        }
+        if (cw < 2) {
+            // this thread's Q row (cw 0) or dO row (cw 1): 256 contiguous bytes, global -> registers -> TMEM
+            const __nv_bfloat16* src = cw == 0 ? p.q + (int64_t)(s0 + m) * p.q_st + (int64_t)h * p.q_sh
+                                               : p.dout + (int64_t)(s0 + m) * p.do_st + (int64_t)h * p.do_sh;
+            const uint32_t dst = lane_base + 384 + cw * 64;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t w[32];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (m < L) v = *reinterpret_cast<const uint4*>(src + half * 64 + g * 8);
+                    w[g * 4] = v.x; w[g * 4 + 1] = v.y; w[g * 4 + 2] = v.z; w[g * 4 + 3] = v.w;
+                }
+                tmem_st32(dst + half * 32, w);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[N8_LOAD]);
+        }
+        const uint32_t ds_a = smem_u32(sdS);
+        for (int j = 0; j < n_tiles; ++j) {
+            const uint32_t ph = (uint32_t)j & 1u;
+            mbar_wait(&bar[N8_SPFULL], ph);
+            tc_fence_after();
+            uint32_t sv[32], dv[32];
+            tmem_ld32_nowait(lane_base + cw * 32, sv);
+            tmem_ld32_nowait(lane_base + 128 + cw * 32, dv);
+            tmem_wait_ld();
+            tc_fence_before();  // S/dP are in registers: release both buffers for tile j+1
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[N8_SEMPTY]);
+            const bool need_mask = (j * N8_BN + N8_BN > L) || (m0 + TC_BM > L) || (p.causal && j * N8_BN + N8_BN > m0);
+            uint32_t pk[16];
+            if (need_mask) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const int n = j * N8_BN + cw * 32 + i;
+                    const bool ok0 = n < L && m < L && (!p.causal || n <= m);
+                    const bool ok1 = n + 1 < L && m < L && (!p.causal || n + 1 <= m);
+                    const float p0 = ok0 ? exp2f(__uint_as_float(sv[i]) * sl2 - lse2) : 0.f;
+                    const float p1 = ok1 ? exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse2) : 0.f;
+                    pk[i >> 1] = f2_to_bf2(p0 * (__uint_as_float(dv[i]) - dl), p1 * (__uint_as_float(dv[i + 1]) - dl));
+                }
+            } else {
+                const float2 sl2v = make_float2(sl2, sl2), nlse = make_float2(-lse2, -lse2), ndl = make_float2(-dl, -dl);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 t = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, nlse);
+                    const float2 u = fadd2(make_float2(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), ndl);
+                    const float2 w = fmul2(make_float2(exp2f(t.x), exp2f(t.y)), u);
+                    pk[i >> 1] = f2_to_bf2(w.x, w.y);
+                }
+            }
+            mbar_wait(&bar[N8_DSEMPTY], ph ^ 1);  // the dS buffer's previous reader (dQ_{j-1}) has retired
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t addr = swz_addr(ds_a, TC_BM, r, cw * 4 + g);
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[g * 4]), "r"(pk[g * 4 + 1]),
+                             "r"(pk[g * 4 + 2]), "r"(pk[g * 4 + 3]) : "memory");
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[N8_DSFULL]);
+        }
+        mbar_wait(&bar[N8_DONE], 0);
+        tc_fence_after();
+        __nv_bfloat16* row = p.dq + (int64_t)(s0 + m) * p.dq_st + (int64_t)h * p.dq_sh;
+        {
+            const int c = cw;
+            uint32_t v[32];
+            tmem_ld32(lane_base + 256 + c * 32, v);
+            if (m < L) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 w;
+                    w.x = f2_to_bf2(__uint_as_float(v[g * 8 + 0]) * p.scale, __uint_as_float(v[g * 8 + 1]) * p.scale);
+                    w.y = f2_to_bf2(__uint_as_float(v[g * 8 + 2]) * p.scale, __uint_as_float(v[g * 8 + 3]) * p.scale);
+                    w.z = f2_to_bf2(__uint_as_float(v[g * 8 + 4]) * p.scale, __uint_as_float(v[g * 8 + 5]) * p.scale);
+                    w.w = f2_to_bf2(__uint_as_float(v[g * 8 + 6]) * p.scale, __uint_as_float(v[g * 8 + 7]) * p.scale);
+                    *reinterpret_cast<uint4*>(row + c * 32 + g * 8) = w;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 constexpr int TB_QS_SS = 3, TB_QS_TS = 5, TB_QS_MAX = 5;  // Q/dO smem ring depth of the dK/dV kernel
 enum { K_LOAD = 0, K_QFULL = 1, K_QEMPTY = K_QFULL + TB_QS_MAX, K_STFULL = K_QEMPTY + TB_QS_MAX, K_STEMPTY = K_STFULL + 2,
        K_PFULL = K_STEMPTY + 2, K_PEMPTY = K_PFULL + 2, K_DONE = K_PEMPTY + 2, K_COUNT = K_DONE + 1 };
@@ -1001,6 +1228,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     const bool pingpong = (causal >> 11) & 1;     // bit 11: softmax warpgroups on alternate tiles
     const bool p16 = (causal >> 12) & 1;          // bit 12: sixteen softmax warps, two groups of eight on alternate tiles
     const bool trace = (causal >> 13) & 1;        // bit 13: debug timeline of block 0 of the dQ kernel (vb200_attn_debug_trace)
+    const bool dq_n128 = (causal >> 14) & 1;      // bit 14: dQ kernel with 128-row K/V tiles (attn_bwd_dq_n128_kernel)
     causal &= 1;
     if (head_dim != 128) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: head_dim must be 128");
     if (q_heads <= 0 || k_heads <= 0 || q_heads % k_heads) return vb200_set_error(VB200_EINVAL, "attn_bwd_tc: Hq % Hk != 0");
@@ -1034,6 +1262,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     }
     const size_t smem_dq = 2 * TC_TILE + 2 * TB_KV_SS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
     const size_t smem_dq_ts = 2 * TB_KV_TS * TB_SMALL + 2 * TB_DS + Q_COUNT * 8 + 16 + 64;
+    const size_t smem_dq_n128 = (2 * N8_KV + 1) * (size_t)N8_TILE + N8_COUNT * 8 + 16 + 64;
     const size_t smem_kv = 2 * TC_TILE + 2 * TB_QS_SS * TB_SMALL + 4 * TB_DS + K_COUNT * 8 + 16 + 2 * 128 * 4 + 64;
     const size_t smem_kv_ts = 2 * TC_TILE + 2 * TB_QS_TS * TB_SMALL + K_COUNT * 8 + 16 + 4 * 128 * 4 + 64;
     static bool attr = false;
@@ -1046,6 +1275,7 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq_ts));
         VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv_ts));
+        VB_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_dq_n128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dq_n128));
         attr = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -1053,7 +1283,8 @@ extern "C" int vb200_attn_varlen_bwd_tc(const void* q, const void* k, const void
     p.nseq = num_seqs;
     dim3 gq(p.tiles * q_heads * num_seqs);
     if (only != 2) {
-        if (ss_operands) attn_bwd_dq_tc_kernel<false, false><<<gq, 320, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
+        if (dq_n128) attn_bwd_dq_n128_kernel<<<gq, 576, smem_dq_n128, s>>>(tmK128, tmV128, p);
+        else if (ss_operands) attn_bwd_dq_tc_kernel<false, false><<<gq, 320, smem_dq, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         else if (p16) attn_bwd_dq_tc_kernel<true, false, true><<<gq, 576, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         else if (pingpong) attn_bwd_dq_tc_kernel<true, true><<<gq, 320, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);
         else attn_bwd_dq_tc_kernel<true, false><<<gq, 320, smem_dq_ts, s>>>(tmQ128, tmdO128, tmK64, tmV64, p);

@@ -555,7 +555,7 @@ struct ScatterArgs {
 
 constexpr int kTileVecs = 8;  // 16-byte vectors per thread per tile: a tile is blockDim * 8 * 16 B = 64 KB of one parameter
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 allgather_scatter_kernel(CommDev c, int ch, int64_t off, int64_t shard_bytes, ScatterArgs a) {
     __shared__ int64_t peer_off[kMaxWorld];
     __shared__ int s_tprefix[kScatterMax + 1];  // 64 KB tiles before parameter i inside one rank's row
@@ -886,6 +886,14 @@ static int check_ch(int ch) {
     if (ch < 0 || ch >= kMaxChannels) return vb200_set_error(VB200_EINVAL, "channel out of range");
     return 0;
 }
+static bool comm_cluster_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VB200_COMM_CLUSTER");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
 static int clamp_ctas(int n) { return n < 1 ? 1 : (n > 2 * kNumSMs ? 2 * kNumSMs : n); }
 
 extern "C" int vb200_comm_barrier(void* comm, int32_t channel, void* stream) {
@@ -1016,7 +1024,28 @@ extern "C" int vb200_allgather_scatter(void* comm, int32_t channel, int64_t regi
             return vb200_set_error(VB200_EINVAL, "allgather_scatter: inconsistent parameter table");
         if ((a.off[i] | a.bytes[i] | (int64_t)(uintptr_t)a.dst[i]) & 15) a.vec_ok = 0;
     }
-    allgather_scatter_kernel<<<clamp_ctas(num_ctas), 512, 0, (cudaStream_t)stream>>>(h->dev, channel, region_offset, shard_bytes, a);
+    // num_ctas counts 512-thread units. Launched as half as many 1024-thread CTAs in clusters of two: the same threads
+    // and bytes in flight, but on a quarter of the TPCs — a communication CTA on an SM keeps the GEMMs' CTA pairs (cuBLAS
+    // 2-SM tcgen05 kernels need a whole TPC, all of its registers and shared memory) off that TPC for as long as it runs.
+    const bool pair = comm_cluster_enabled();  // VB200_COMM_CLUSTER=0: plain 512-thread CTAs (debugging / A-B)
+    int ctas = pair ? (clamp_ctas(num_ctas) + 1) / 2 : clamp_ctas(num_ctas);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(pair ? 1024 : 512);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = (cudaStream_t)stream;
+    cfg.numAttrs = 0;
+    if (pair && ctas >= 2) {
+        ctas &= ~1;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cfg.gridDim = dim3(ctas);
+    VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, allgather_scatter_kernel, h->dev, (int)channel, region_offset, shard_bytes, a));
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
@@ -1049,14 +1078,28 @@ extern "C" int vb200_reduce_scatter_push_bf16(void* comm, int32_t channel, int64
         acc += a.chunk[i];
     }
     if (acc != row_elems) return vb200_set_error(VB200_EINVAL, "reduce_scatter_push: chunks do not add up to the row");
-    const int g = clamp_ctas(num_ctas);
-    cudaStream_t st = (cudaStream_t)stream;
+    int g = clamp_ctas(num_ctas);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(512);
+    cfg.stream = (cudaStream_t)stream;
+    if (comm_cluster_enabled() && g >= 2) {  // CTA pairs share a TPC (see vb200_allgather_scatter)
+        g &= ~1;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cfg.gridDim = dim3(g);
     const char* gen = getenv("VB200_RS_GENERIC");
+    const int ch32 = (int)channel;
     switch ((gen && gen[0] == '1') ? 0 : h->dev.world) {
-        case 1: reduce_scatter_push_bf16_kernel<1><<<g, 512, 0, st>>>(h->dev, channel, region_offset, a, scale, out); break;
-        case 2: reduce_scatter_push_bf16_kernel<2><<<g, 512, 0, st>>>(h->dev, channel, region_offset, a, scale, out); break;
-        case 4: reduce_scatter_push_bf16_kernel<4><<<g, 512, 0, st>>>(h->dev, channel, region_offset, a, scale, out); break;
-        default: reduce_scatter_push_bf16_kernel<0><<<g, 512, 0, st>>>(h->dev, channel, region_offset, a, scale, out); break;
+        case 1: VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<1>, h->dev, ch32, region_offset, a, scale, out)); break;
+        case 2: VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<2>, h->dev, ch32, region_offset, a, scale, out)); break;
+        case 4: VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<4>, h->dev, ch32, region_offset, a, scale, out)); break;
+        default: VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<0>, h->dev, ch32, region_offset, a, scale, out)); break;
     }
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();

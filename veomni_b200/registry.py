@@ -217,6 +217,23 @@ def register(force: bool = True) -> bool:
     from . import async_ulysses
 
     async_ulysses.install()
+    # cross-entropy: besides the OpSlot, HF's LOSS_MAPPING is filled through a closed name list
+    # (veomni/ops/kernels/cross_entropy/__init__.py:336-353,480-516) — add "b200" to it
+    try:
+        import veomni.ops.kernels.cross_entropy as ref_ce
+
+        from .cross_entropy import b200_cross_entropy
+
+        if not getattr(ref_ce._resolve_cross_entropy_fn, "_vb200", False):
+            _orig_resolve = ref_ce._resolve_cross_entropy_fn
+
+            def _resolve_cross_entropy_fn(impl: str):
+                return b200_cross_entropy if impl == IMPL_NAME else _orig_resolve(impl)
+
+            _resolve_cross_entropy_fn._vb200 = True
+            ref_ce._resolve_cross_entropy_fn = _resolve_cross_entropy_fn
+    except Exception:  # noqa: BLE001
+        pass
     # fused MoE raw pointer (veomni/ops/kernels/moe/__init__.py:62-108)
     try:
         import veomni.ops.kernels.moe as ref_moe
