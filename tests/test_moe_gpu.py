@@ -81,7 +81,7 @@ def _ragged(G, total, seed, empties=()):
 
 @pytest.mark.parametrize("G,total,N,K", [(1, 128, 128, 64), (3, 200, 128, 64), (4, 37, 64, 128), (8, 1000, 256, 192),
                                          (16, 4096, 1536, 2048), (128, 4096, 2048, 768), (5, 300, 72, 40)])
-@pytest.mark.parametrize("variant", [1, 2])  # 1: tokens on the MMA M side, 2: tokens on the N side (the default)
+@pytest.mark.parametrize("variant", [1, 2, 3])  # 1: tokens on the MMA M side, 2: tokens on N (default), 3: 2-CTA (cta_group::2) tokens on N
 def test_group_gemm_nt_nn_vs_oracle(cuda_dev, G, total, N, K, variant, monkeypatch):
     from veomni_b200 import moe as M
     from veomni_b200.moe import group_gemm_same_nk

@@ -44,7 +44,7 @@ BWD_IMPL = os.environ.get("VB200_ATTN_BWD", "tc")
 # EXPERIMENTAL (not yet run on hardware): eight softmax warps in the tcgen05 forward, see attn_fwd_tc_kernel<W8>
 FWD_W8 = os.environ.get("VB200_ATTN_FWD_W8", "1") == "1"  # eight softmax warps (validated on B200: 173 vs 178 us at T=4096)
 BWD_PP = os.environ.get("VB200_ATTN_BWD_PP", "0") == "1"  # softmax warpgroups on alternate tiles ("ping-pong")
-BWD_DQ_N128 = os.environ.get("VB200_ATTN_BWD_DQ_N128", "0") == "1"  # dQ kernel with 128-row K/V tiles (N = 128 MMAs)
+BWD_DQ_N128 = os.environ.get("VB200_ATTN_BWD_DQ_N128", "1") == "1"  # dQ kernel with 128-row K/V tiles (N = 128 MMAs); bit-identical, -25 % (B200)
 BWD_TRACE = False  # debugging: record the dQ kernel's hand-off timeline (tools/attn_trace.py)
 BWD_P16 = os.environ.get("VB200_ATTN_BWD_P16", "0") == "1"  # sixteen softmax warps: two groups of eight on alternate tiles
 BWD_DQ_SS = False  # True: dQ kernel with every MMA operand in shared memory (cross-check of the A-in-TMEM default)

@@ -447,6 +447,237 @@ group_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
 }
 
+
+// ================================================================================================================
+// 2-CTA ("cta_group::2") form of the swapped-operand kernel: a cluster of two CTAs (one TPC) computes a
+// 256-feature x <=256-token tile. Each CTA stages HALF of both operands — its 128 weight rows and half of the token rows —
+// and the leader CTA's single thread issues tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and
+// writes each CTA's 128 x ntok half of the accumulator into that CTA's TMEM. Per FLOP a CTA moves (16 + <=16) KB per
+// k-block instead of (16 + <=32): the 1-CTA kernels sit on the L2 -> shared-memory path (ncu), this is the
+// lever cuBLAS / CUTLASS pull with their 256x256 2-SM tiles.
+// Barriers: full[s] lives in the leader only (both CTAs' TMA loads complete on it: cp.async.bulk.tensor ...cta_group::2 with
+// the barrier's shared::cluster address of CTA 0); empty[s] and tfull[a] exist in both CTAs and are signalled by the leader's
+// tcgen05.commit ...multicast::cluster; tempty[a] lives in the leader and counts the epilogue warps of BOTH CTAs (the peer's
+// arrive remotely). The CTAs of a cluster stay together until the last MMA has retired (cluster barrier at both ends).
+// ================================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot_in_smem, uint32_t ncols) {  // whole warp, in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t base, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+// TMA loads whose completion bytes go to the barrier at the same shared-memory offset in CTA 0 of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_bo_2sm(uint32_t tmem_d, uint32_t a16, uint32_t a_off, uint32_t a_lbo, uint32_t a_sbo,
+                                                uint32_t b16, uint32_t b_off, uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc,
+                                                uint32_t accumulate) {
+    const uint32_t a_lo = a16 + ((a_off >> 4) + (((a_lbo >> 4) & 0x3FFFu) << 16));
+    const uint32_t b_lo = b16 + ((b_off >> 4) + (((b_lbo >> 4) & 0x3FFFu) << 16));
+    const uint32_t a_hi = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    const uint32_t b_hi = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta0(uint64_t* bar) {  // arrive on the barrier at this offset in CTA 0
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int G2_BM = 256;  // weight rows per cluster tile (128 per CTA)
+
+__device__ __forceinline__ bool get_swap2_tile(int t, const int* tile_start, const GGParams& p, int n_wt, SwapTile& ti) {
+    if (t >= tile_start[p.G]) return false;
+    int lo = 0, hi = p.G - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tile_start[mid + 1] <= t) lo = mid + 1;
+        else hi = mid;
+    }
+    ti.g = lo;
+    const int r = t - tile_start[lo];
+    ti.tt = r / n_wt;
+    ti.wt = r - ti.tt * n_wt;
+    const int s = lo ? p.cumsum[lo - 1] : 0;
+    ti.row0 = s + ti.tt * GS_TOK;
+    ti.rows_valid = min(GS_TOK, p.cumsum[lo] - ti.row0);
+    ti.ntok = (ti.rows_valid + 31) & ~31;  // MMA N: a multiple of 32 so that each CTA's half is a multiple of 16
+    return true;
+}
+
+template <bool NN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GG_THREADS, 1)
+group_gemm_swap2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const GGParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* stages = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GG_STAGES * GS_STAGE_BYTES);
+    uint64_t* empty = full + GG_STAGES;
+    uint64_t* tfull = empty + GG_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    int* tile_start = reinterpret_cast<int*>(tmem_slot + 2);  // [G+1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int n_wt = (p.N + G2_BM - 1) / G2_BM;
+    const int kblocks = (p.K + GG_BK - 1) / GG_BK;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int g = 0; g < p.G; ++g) {
+            tile_start[g] = run;
+            const int rows = p.cumsum[g] - (g ? p.cumsum[g - 1] : 0);
+            run += ((rows + GS_TOK - 1) / GS_TOK) * n_wt;
+        }
+        tile_start[p.G] = run;
+        for (int s = 0; s < GG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * GG_EPI_WARPS); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 1) tmem_alloc2(tmem_slot, 2 * GS_TOK);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit / 2-SM TMA
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs: own 128 weight rows, own half of the token rows) =====
+        if (elect_one_sync()) {
+            int s = 0;
+            uint32_t ph = 0;
+            SwapTile ti;
+            for (int t = cluster_id; get_swap2_tile(t, tile_start, p, n_wt, ti); t += n_clusters) {
+                const int half_tok = ti.ntok >> 1;                  // token rows staged by each CTA (multiple of 16)
+                const int nbox = (half_tok + 63) >> 6;               // 64-row boxes per CTA
+                const uint32_t bytes_cta = GS_BM * GG_BK * 2 + nbox * 64 * GG_BK * 2;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* sa = stages + s * GS_STAGE_BYTES;
+                    uint8_t* sb = sa + GS_BM * GG_BK * 2;
+                    if (crank == 0) mbar_expect_tx(&full[s], 2 * bytes_cta);  // the pair's bytes land on the leader's barrier
+                    const int w0 = ti.wt * G2_BM + (int)crank * GS_BM;
+                    if (!NN) {
+                        tma_load_3d_2sm(sa, &tmW, kb * GG_BK, w0, ti.g, &full[s]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < GS_BM / 64; ++i)
+                            tma_load_3d_2sm(sa + i * GG_BK * 128, &tmW, w0 + i * 64, kb * GG_BK, ti.g, &full[s]);
+                    }
+                    const int r0 = ti.row0 + (int)crank * half_tok;
+                    for (int i = 0; i < nbox; ++i)
+                        tma_load_2d_2sm(sb + i * 64 * 128, &tmX, kb * GG_BK, r0 + i * 64, &full[s]);
+                    if (++s == GG_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (crank == 0) {
+            int s = 0, acc = 0;
+            uint32_t ph = 0, aph = 0;
+            SwapTile ti;
+            for (int t = cluster_id; get_swap2_tile(t, tile_start, p, n_wt, ti); t += n_clusters) {
+                const uint32_t idesc = umma_idesc(NN ? 1 : 0, 0, G2_BM, ti.ntok);
+                mbar_wait(&tempty[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * GS_TOK;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    uint8_t* sa = stages + s * GS_STAGE_BYTES;
+                    uint8_t* sb = sa + GS_BM * GG_BK * 2;
+                    if (elect_one_sync()) {
+                        const uint32_t a_addr = smem_u32(sa), b_addr = smem_u32(sb);
+#pragma unroll
+                        for (int k = 0; k < GG_BK / 16; ++k) {
+                            const uint32_t a_off = NN ? k * 16 * 128 : k * 32, a_lbo = NN ? GG_BK * 128 : 16;
+                            umma_f16_bo_2sm(tmem_d, a_addr >> 4, a_off, a_lbo, 1024, b_addr >> 4, k * 32, 16, 1024, idesc, (kb | k) ? 1u : 0u);
+                        }
+                        umma_commit_2sm(&empty[s]);
+                        if (kb == kblocks - 1) umma_commit_2sm(&tfull[acc]);
+                    }
+                    __syncwarp();
+                    if (++s == GG_STAGES) { s = 0; ph ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): lane = output feature of this CTA's 128, column = token =====
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int acc = 0;
+        uint32_t aph = 0;
+        SwapTile ti;
+        for (int t = cluster_id; get_swap2_tile(t, tile_start, p, n_wt, ti); t += n_clusters) {
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const int f = ti.wt * G2_BM + (int)crank * GS_BM + q * 32 + lane;
+            const bool f_ok = f < p.N;
+            __nv_bfloat16* cbase = p.C + (int64_t)ti.row0 * p.N + f;
+            const int nch = (ti.rows_valid + 31) >> 5;
+#pragma unroll 1
+            for (int c = half; c < nch; c += 2) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GS_TOK + c * 32, v);
+                if (f_ok) {
+                    const int left = ti.rows_valid - c * 32;
+                    __nv_bfloat16* cp = cbase + (int64_t)c * 32 * p.N;
+                    if (left >= 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cp[(int64_t)j * p.N] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < left) cp[(int64_t)j * p.N] = __float2bfloat16_rn(__uint_as_float(v[j]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta0(&tempty[acc]);
+            if (++acc == 2) { acc = 0; aph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's shared memory and TMEM stay valid until the leader's last MMA has been consumed
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, 2 * GS_TOK);
+    }
+}
+
 static size_t gg_smem_bytes(int G) {
     return (size_t)GG_STAGES * GG_STAGE_BYTES + (2 * GG_STAGES + 4) * 8 + 16 + (size_t)(G + 1) * 4 + 64;
 }
@@ -477,6 +708,29 @@ extern "C" int vb200_group_gemm(int32_t mode, const void* a, const void* b, void
     if (swap_mode < 0) {
         const char* e = getenv("VB200_GG_SWAP");
         swap_mode = (e && e[0] == '0') ? 0 : 1;  // default on (validated on B200: bit-compatible results, fc1 +4 %, fc2 +11 %, dgrad +6 %)
+    }
+    static int two_cta = -1;
+    if (two_cta < 0) {
+        const char* e = getenv("VB200_GG_2CTA");
+        two_cta = (e && e[0] == '1') ? 1 : 0;  // default off until validated on hardware
+    }
+    if (mode != GG_TN && (variant == 3 || (variant == 0 && two_cta))) {
+        const size_t smem_sw = (size_t)GG_STAGES * GS_STAGE_BYTES + (2 * GG_STAGES + 4) * 8 + 16 + (size_t)(num_groups + 1) * 4 + 64;
+        if ((rc = make_tmap_2d(&tmA, a, k, rows, k, 64))) return rc;  // tokens [rows, K], box 64 x 64
+        if (mode == GG_NT) {
+            if ((rc = make_tmap_3d_box(&tmB, b, k, n, num_groups, k, (uint64_t)n * k, 64, GS_BM))) return rc;
+            static bool attr = false;
+            if (!attr) { VB_CUDA_TRY(cudaFuncSetAttribute(group_gemm_swap2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+            group_gemm_swap2_kernel<false><<<kNumSMs, GG_THREADS, smem_sw, st>>>(tmA, tmB, p);
+        } else {
+            if ((rc = make_tmap_3d_box(&tmB, b, n, k, num_groups, n, (uint64_t)n * k, 64, GG_BK))) return rc;
+            static bool attr = false;
+            if (!attr) { VB_CUDA_TRY(cudaFuncSetAttribute(group_gemm_swap2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+            group_gemm_swap2_kernel<true><<<kNumSMs, GG_THREADS, smem_sw, st>>>(tmA, tmB, p);
+        }
+        vb200_count_launch(1);
+        VB_HOST_CHECK_LAUNCH();
+        return VB200_OK;
     }
     if (mode != GG_TN && (variant == 2 || (variant == 0 && swap_mode))) {
         // tokens on the MMA N side (see group_gemm_swap_kernel)

@@ -240,14 +240,16 @@ def register(force: bool = True) -> bool:
 
         from .moe import fused_moe_forward
 
-        _orig = ref_moe.apply_veomni_fused_moe_patch
+        _orig = getattr(ref_moe.apply_veomni_fused_moe_patch, "_vb200_orig", ref_moe.apply_veomni_fused_moe_patch)
 
-        def apply_veomni_fused_moe_patch(moe_implementation: str = "fused", *a, **k):
-            if moe_implementation in (IMPL_NAME, f"fused_{IMPL_NAME}"):
+        def apply_veomni_fused_moe_patch(fused_moe_kernel: str = "triton", *a, **k):
+            # same keyword as the reference (ops/kernels/moe/__init__.py:60; called as fused_moe_kernel=... by auto.py:99)
+            if fused_moe_kernel in (IMPL_NAME, f"fused_{IMPL_NAME}"):
                 ref_moe._fused_moe_forward = fused_moe_forward
                 return
-            return _orig(moe_implementation, *a, **k)
+            return _orig(fused_moe_kernel, *a, **k)
 
+        apply_veomni_fused_moe_patch._vb200_orig = _orig
         ref_moe.apply_veomni_fused_moe_patch = apply_veomni_fused_moe_patch
     except Exception:  # noqa: BLE001  (reference without the MoE package on this platform)
         pass
