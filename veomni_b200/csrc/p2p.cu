@@ -404,35 +404,27 @@ all_to_all_kernel(CommDev c, int ch, int64_t off, A2AArgs args) {
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t GW = ((int64_t)gridDim.x * blockDim.x) >> 5;
     constexpr int R = 8;  // row segments in flight per warp (one 16 B load per lane each)
+    // Loop order: descriptor, peer, rows. Peer and descriptor are uniform per sweep, so a row costs two adds — the first
+    // version decoded (peer, row) from a flat item index with a 64-bit division per item and was instruction-bound on the
+    // 512-byte k/v segments of the Ulysses exchange (228-304 GB/s).
     for (int di = 0; di < args.n; ++di) {
         const A2ADesc& d = args.d[di];
         const int vec_per_seg = (int)(d.seg_bytes >> 4);
-        const int64_t items = d.rows * c.world;  // (peer slot q, row)
-        for (int64_t it0 = gw * R; it0 < items; it0 += GW * R) {
-            const uint4* srcp[R];
-            uint4* dstp[R];
+        for (int q = 0; q < c.world; ++q) {
+            const int p = (c.rank + q) % c.world;  // staggered over sources
+            const uint8_t* sbase = c.data[p] + peer_off[p] + d.src_off + (int64_t)c.rank * d.src_rank_stride;
+            uint8_t* dbase = d.dst + (int64_t)p * d.dst_peer_stride;
+            for (int64_t row0 = gw * R; row0 < d.rows; row0 += GW * R) {
+                const int nr = (int)((d.rows - row0) < R ? (d.rows - row0) : R);
+                for (int v = lane; v < vec_per_seg; v += 32) {
+                    uint4 val[R];
 #pragma unroll
-            for (int u = 0; u < R; ++u) {
-                const int64_t it = it0 + u;
-                srcp[u] = nullptr;
-                dstp[u] = nullptr;
-                if (it < items) {
-                    const int q = (int)(it / d.rows);
-                    const int64_t row = it - (int64_t)q * d.rows;
-                    const int p = (c.rank + q) % c.world;  // staggered over sources
-                    srcp[u] = reinterpret_cast<const uint4*>(c.data[p] + peer_off[p] + d.src_off +
-                                                             (int64_t)c.rank * d.src_rank_stride + row * d.src_row_stride);
-                    dstp[u] = reinterpret_cast<uint4*>(d.dst + (int64_t)p * d.dst_peer_stride + row * d.dst_row_stride);
+                    for (int u = 0; u < R; ++u)
+                        if (u < nr) val[u] = ldg_v4(sbase + (row0 + u) * d.src_row_stride + ((int64_t)v << 4));
+#pragma unroll
+                    for (int u = 0; u < R; ++u)
+                        if (u < nr) stg_v4(dbase + (row0 + u) * d.dst_row_stride + ((int64_t)v << 4), val[u]);
                 }
-            }
-            for (int v = lane; v < vec_per_seg; v += 32) {
-                uint4 val[R];
-#pragma unroll
-                for (int u = 0; u < R; ++u)
-                    if (srcp[u]) val[u] = ldg_v4(srcp[u] + v);
-#pragma unroll
-                for (int u = 0; u < R; ++u)
-                    if (dstp[u]) dstp[u][v] = val[u];
             }
         }
     }
