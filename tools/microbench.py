@@ -83,6 +83,19 @@ def bench_rmsnorm(dev, iters):
                               dw.data_ptr(), T, H, st)
 
     report("rmsnorm_bwd[4096x4096]", time_fn(bwd, bsets, iters), nbytes=3 * T * H * 2)
+    # fused residual-add + norm (the decoder layer's two norms): x, residual -> h, y ; dy, h, dh -> dx
+    asets = [(x, y, r, torch.empty_like(x), torch.empty_like(x)) for (x, y, r) in sets]
+
+    def afwd(x, res, r, h, y):
+        lib.vb200_add_rmsnorm_fwd(x.data_ptr(), res.data_ptr(), w.data_ptr(), h.data_ptr(), y.data_ptr(), r.data_ptr(), T, H, 1e-6, st)
+
+    report("add_rmsnorm_fwd[4096x4096]", time_fn(afwd, asets, iters), nbytes=4 * T * H * 2)
+
+    def abwd(dy, x, r, dres, dx):
+        lib.vb200_rmsnorm_bwd_add(dy.data_ptr(), x.data_ptr(), w.data_ptr(), r.data_ptr(), dres.data_ptr(), dx.data_ptr(),
+                                  part.data_ptr(), dw.data_ptr(), T, H, st)
+
+    report("rmsnorm_bwd_add[4096x4096]", time_fn(abwd, asets, iters), nbytes=4 * T * H * 2)
     # per-head norm shape (q heads)
     R, C = 4096 * 40, 128
     hs = [(torch.randn(R, C, device=dev, dtype=BF), torch.empty(R, C, device=dev, dtype=BF),

@@ -108,6 +108,37 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     u.z = f2_to_bf2(f[4], f[5]); u.w = f2_to_bf2(f[6], f[7]);
     return u;
 }
+// bf16x2 * bf16x2 -> bf16x2, one rounding (the product of two bf16 values is exact in fp32, so this equals the
+// reference's fp32 multiply followed by `.to(bfloat16)`); SASS HMUL2.BF16.
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// Sum of squares of the 8 bf16 values of one 16-byte vector into two packed accumulators (FFMA2). Every RMSNorm
+// forward that must agree bit-for-bit (plain and fused-add) uses this one accumulation order.
+__device__ __forceinline__ void sumsq8(const uint4& u, float2& acc0, float2& acc1) {
+    const float2 a = bf2_to_f2(u.x), b = bf2_to_f2(u.y), c = bf2_to_f2(u.z), d = bf2_to_f2(u.w);
+    acc0 = ffma2(a, a, acc0);
+    acc1 = ffma2(b, b, acc1);
+    acc0 = ffma2(c, c, acc0);
+    acc1 = ffma2(d, d, acc1);
+}
+// y = w * bf16(x * rs) on one vector of 8 (two roundings, as Qwen3RMSNorm): FMUL2 + F2FP pack + HMUL2.BF16.
+__device__ __forceinline__ uint4 norm_scale8(const uint4& u, const uint4& wv, float2 rs2) {
+    uint4 o;
+    float2 t;
+    t = fmul2(bf2_to_f2(u.x), rs2); o.x = bf2_mul(wv.x, f2_to_bf2(t.x, t.y));
+    t = fmul2(bf2_to_f2(u.y), rs2); o.y = bf2_mul(wv.y, f2_to_bf2(t.x, t.y));
+    t = fmul2(bf2_to_f2(u.z), rs2); o.z = bf2_mul(wv.z, f2_to_bf2(t.x, t.y));
+    t = fmul2(bf2_to_f2(u.w), rs2); o.w = bf2_mul(wv.w, f2_to_bf2(t.x, t.y));
+    return o;
+}
+// Programmatic dependent launch: the dependent grid may start once every CTA of the primary has executed
+// launch_dependents (or exited); its reads of the primary's results must come after griddep_wait().
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Round an fp32 value to bf16 precision and back (mirrors `.to(bfloat16)` in the reference).
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 

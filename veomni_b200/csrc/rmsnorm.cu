@@ -69,41 +69,32 @@ rmsnorm_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
         const int s = it % kFwdStages;
         const uint32_t parity = (uint32_t)(it / kFwdStages) & 1u;
         uint4* buf = reinterpret_cast<uint4*>(my_bufs + (size_t)s * row_bytes);
+        // Refill the buffer stored one iteration ago BEFORE working on this row: the load of the next row then overlaps
+        // this row's arithmetic (the store only has to have been read out of shared memory, which takes well under a
+        // microsecond, not to have landed).
+        if (lane == 0 && it >= 1) {
+            bulk_wait_read<0>();
+            const int ps = (it + kFwdStages - 1) % kFwdStages;
+            const int64_t nr = r + (int64_t)(kFwdStages - 1) * GW;
+            if (nr < rows) {
+                mbar_expect_tx(&my_bars[ps], row_bytes);
+                bulk_g2s(my_bufs + (size_t)ps * row_bytes, x + nr * cols, row_bytes, &my_bars[ps]);
+            }
+        }
         mbar_wait(&my_bars[s], parity);
 
-        float ss = 0.f;
-        for (int v = lane; v < nvec; v += 32) {
-            float f[8];
-            unpack8(buf[v], f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ss = fmaf(f[i], f[i], ss);
-        }
-        ss = warp_sum(ss);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        for (int v = lane; v < nvec; v += 32) sumsq8(buf[v], acc0, acc1);
+        const float ss = warp_sum((acc0.x + acc0.y) + (acc1.x + acc1.y));
         const float rs = rsqrtf(ss * inv_cols + eps);
-        for (int v = lane; v < nvec; v += 32) {
-            float f[8], g[8];
-            unpack8(buf[v], f);
-            unpack8(w_s[v], g);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = g[i] * round_bf16(f[i] * rs);
-            buf[v] = pack8(f);
-        }
+        const float2 rs2 = make_float2(rs, rs);
+        for (int v = lane; v < nvec; v += 32) buf[v] = norm_scale8(buf[v], w_s[v], rs2);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
             rstd[r] = rs;
             bulk_s2g(y + r * cols, buf, row_bytes);
             bulk_commit();
-            // The buffer written one iteration ago may be refilled once its store has been read.
-            if (it >= 1) {
-                bulk_wait_read<1>();
-                const int ps = (it - 1) % kFwdStages;
-                const int64_t nr = r - GW + (int64_t)kFwdStages * GW;
-                if (nr < rows) {
-                    mbar_expect_tx(&my_bars[ps], row_bytes);
-                    bulk_g2s(my_bufs + (size_t)ps * row_bytes, x + nr * cols, row_bytes, &my_bars[ps]);
-                }
-            }
         }
         __syncwarp();
     }
@@ -257,31 +248,28 @@ add_rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     for (int64_t row = wid; row < rows; row += nw) {
         const __nv_bfloat16 *xr = x + row * H, *rr = res + row * H;
         uint4 hv[NCH];
-        float ss = 0.f;
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
-            float a[8], b[8];
-            unpack8(ldg_stream(xr + (k * 32 + lane) * 8), a);
-            unpack8(ldg_stream(rr + (k * 32 + lane) * 8), b);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                a[i] = round_bf16(a[i] + b[i]);
-                ss = fmaf(a[i], a[i], ss);
-            }
-            hv[k] = pack8(a);
-            stg_stream(h_out + row * H + (k * 32 + lane) * 8, hv[k]);
+            const uint4 a = ldg_stream(xr + (k * 32 + lane) * 8), b = ldg_stream(rr + (k * 32 + lane) * 8);
+            float2 t;
+            uint4 h;  // h = bf16(x + residual): fp32 add, one rounding (as torch adds two bf16 tensors)
+            t = fadd2(bf2_to_f2(a.x), bf2_to_f2(b.x)); h.x = f2_to_bf2(t.x, t.y);
+            t = fadd2(bf2_to_f2(a.y), bf2_to_f2(b.y)); h.y = f2_to_bf2(t.x, t.y);
+            t = fadd2(bf2_to_f2(a.z), bf2_to_f2(b.z)); h.z = f2_to_bf2(t.x, t.y);
+            t = fadd2(bf2_to_f2(a.w), bf2_to_f2(b.w)); h.w = f2_to_bf2(t.x, t.y);
+            sumsq8(h, acc0, acc1);
+            hv[k] = h;
+            stg_stream(h_out + row * H + (k * 32 + lane) * 8, h);
         }
-        ss = warp_sum(ss);
+        const float ss = warp_sum((acc0.x + acc0.y) + (acc1.x + acc1.y));
         const float rs = rsqrtf(ss * (1.0f / (float)H) + eps);
         if (lane == 0) rstd[row] = rs;
+        const float2 rs2 = make_float2(rs, rs);
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
-            float a[8], wf[8];
-            unpack8(hv[k], a);
-            unpack8(*reinterpret_cast<const uint4*>(w + (k * 32 + lane) * 8), wf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = wf[i] * round_bf16(a[i] * rs);
-            stg_stream(y + row * H + (k * 32 + lane) * 8, pack8(a));
+            const uint4 wv = *reinterpret_cast<const uint4*>(w + (k * 32 + lane) * 8);
+            stg_stream(y + row * H + (k * 32 + lane) * 8, norm_scale8(hv[k], wv, rs2));
         }
     }
 }
@@ -361,6 +349,113 @@ rmsnorm_bwd_wide_add_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfl
     }
 }
 
+// Wide rows, bulk-async staged (the default for cols <= 8192): as above the CTA owns one row at a time and thread t owns
+// vector t, but the dy / x (/ dh) rows arrive through a ring of `stages` shared-memory slots filled by 1-D bulk copies
+// (TMA engine, SASS UBLKCP) that complete on one mbarrier per slot, so `stages` rows of loads are in flight per CTA
+// instead of the one row a register prefetch could hold (the register version reached 0.40-0.53 of the HBM stream).
+// The row's reduction barrier doubles as the slot's "consumed" signal: thread 0 refills it right after. Arithmetic is
+// on packed fp32 pairs (FMUL2/FFMA2); dx leaves through 16-byte streaming stores.
+constexpr int kBwdMaxStages = 8;
+
+template <int THREADS, bool ADD>
+__global__ void __launch_bounds__(THREADS)
+rmsnorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                        const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd,
+                        const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+                        float* __restrict__ dw_partial, int64_t rows, int cols, int stages) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int NW = THREADS / 32;
+    constexpr int NSRC = ADD ? 3 : 2;
+    __shared__ float red[2][NW];
+    __shared__ __align__(8) uint64_t full[kBwdMaxStages];
+    griddep_launch_dependents();  // the column-sum grid may be scheduled early; it waits for this grid's results
+    const int nvec = cols >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row_bytes = (uint32_t)cols * 2u, stage_bytes = NSRC * row_bytes;
+    const bool act = (int)threadIdx.x < nvec;
+    const int64_t G = gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int s, int64_t r) {
+        uint8_t* dst = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full[s], stage_bytes);
+        bulk_g2s(dst, dy + r * cols, row_bytes, &full[s]);
+        bulk_g2s(dst + row_bytes, x + r * cols, row_bytes, &full[s]);
+        if (ADD) bulk_g2s(dst + 2 * row_bytes, dres + r * cols, row_bytes, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < stages; ++s) {
+            const int64_t r = blockIdx.x + (int64_t)s * G;
+            if (r < rows) issue(s, r);
+        }
+    float2 wf[4], dwacc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wf[i] = dwacc[i] = make_float2(0.f, 0.f);
+    if (act) {
+        const uint4 wv = reinterpret_cast<const uint4*>(w)[threadIdx.x];
+        wf[0] = bf2_to_f2(wv.x); wf[1] = bf2_to_f2(wv.y); wf[2] = bf2_to_f2(wv.z); wf[3] = bf2_to_f2(wv.w);
+    }
+    const float inv_cols = 1.0f / (float)cols;
+    int it = 0, s = 0;
+    uint32_t parity = 0;
+    for (int64_t r = blockIdx.x; r < rows; r += G, ++it) {
+        const float rs = rstd[r];
+        mbar_wait(&full[s], parity);
+        const uint4* slot = reinterpret_cast<const uint4*>(smem + (size_t)s * stage_bytes);
+        float2 g[4], xh[4];
+        uint4 dr = make_uint4(0u, 0u, 0u, 0u);
+        float2 dot2 = make_float2(0.f, 0.f);
+        if (act) {
+            const uint4 dv = slot[threadIdx.x], xv = slot[nvec + threadIdx.x];
+            if (ADD) dr = slot[2 * nvec + threadIdx.x];
+            const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w}, xu[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float2 rs2 = make_float2(rs, rs);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 d = bf2_to_f2(du[i]);
+                xh[i] = fmul2(bf2_to_f2(xu[i]), rs2);
+                g[i] = fmul2(d, wf[i]);
+                dot2 = ffma2(g[i], xh[i], dot2);
+                dwacc[i] = ffma2(d, bf2_to_f2(f2_to_bf2(xh[i].x, xh[i].y)), dwacc[i]);  // dy * bf16(xhat)
+            }
+        }
+        float dot = warp_sum(dot2.x + dot2.y);
+        if (lane == 0) red[it & 1][warp] = dot;
+        __syncthreads();  // every thread has read slot s
+        if (threadIdx.x == 0) {
+            const int64_t nr = r + (int64_t)stages * G;
+            if (nr < rows) issue(s, nr);
+        }
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) tot += red[it & 1][i];
+        if (act) {
+            const float2 nc2 = make_float2(-tot * inv_cols, -tot * inv_cols), rs2 = make_float2(rs, rs);
+            uint32_t o[4];
+            const uint32_t e[4] = {dr.x, dr.y, dr.z, dr.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 t = fmul2(rs2, ffma2(xh[i], nc2, g[i]));  // rs * (g - xhat * c)
+                o[i] = f2_to_bf2(t.x, t.y);
+                if (ADD) {  // bf16(bf16(dx) + dh): autograd's accumulation of two bf16 gradients
+                    const float2 u = fadd2(bf2_to_f2(o[i]), bf2_to_f2(e[i]));
+                    o[i] = f2_to_bf2(u.x, u.y);
+                }
+            }
+            stg_stream(dx + r * cols + (int64_t)threadIdx.x * 8, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+        if (++s == stages) { s = 0; parity ^= 1u; }
+    }
+    if (act) {
+        float* dst = dw_partial + (int64_t)blockIdx.x * cols + (int64_t)threadIdx.x * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(dwacc[0].x, dwacc[0].y, dwacc[1].x, dwacc[1].y);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(dwacc[2].x, dwacc[2].y, dwacc[3].x, dwacc[3].y);
+    }
+}
+
 // Narrow rows: TPR lanes per row, CTA of 256 threads handles 256/TPR rows per iteration.
 template <int TPR>
 __global__ void __launch_bounds__(256)
@@ -424,6 +519,7 @@ colsum_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
     float t = 0.f;
+    griddep_wait();  // launched with programmatic stream serialization right behind the kernel that writes `partial`
     if (c < cols)
         for (int64_t p = y; p < nparts; p += 8) t += partial[p * cols + c];
     red[y][x] = t;
@@ -436,6 +532,24 @@ colsum_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_
     }
 }
 
+// Wide-row backward configuration: threads per CTA (one 16-byte vector per thread), CTAs per SM and ring depth.
+struct BwdCfg {
+    int threads, ctas_per_sm, stages;
+    size_t smem;
+};
+static BwdCfg bwd_cfg(int cols, bool add) {
+    const int nvec = cols >> 3;
+    BwdCfg c;
+    c.threads = nvec <= 128 ? 128 : nvec <= 256 ? 256 : nvec <= 512 ? 512 : 1024;
+    c.ctas_per_sm = 2048 / c.threads;
+    if (c.ctas_per_sm > 8) c.ctas_per_sm = 8;
+    const size_t stage = (size_t)(add ? 3 : 2) * cols * 2;
+    const int st = (int)((200 * 1024 / c.ctas_per_sm) / stage);
+    c.stages = st > 6 ? 6 : st < 2 ? 2 : st;
+    c.smem = stage * c.stages;
+    return c;
+}
+
 static int bwd_grid(int64_t rows, int cols) {
     const int nvec = cols >> 3;
     int64_t g;
@@ -445,10 +559,55 @@ static int bwd_grid(int64_t rows, int cols) {
         const int groups = 256 / tpr;
         g = (rows + groups - 1) / groups;
         if (g > 4 * kNumSMs) g = 4 * kNumSMs;
+    } else if (nvec <= 1024) {
+        const int64_t cap = (int64_t)bwd_cfg(cols, false).ctas_per_sm * kNumSMs;  // the fused-add variant uses the same grid
+        g = rows < cap ? rows : cap;
     } else {
         g = rows < 2 * kNumSMs ? rows : 2 * kNumSMs;
     }
     return (int)(g < 1 ? 1 : g);
+}
+
+// out = column sums of the [nparts, cols] partials, launched as a programmatic dependent of the kernel before it.
+static cudaError_t launch_colsum(const float* partial, float* out, int64_t nparts, int cols, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((cols + 31) / 32));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, colsum_kernel, partial, out, nparts, cols);
+}
+
+template <int THREADS, bool ADD>
+static cudaError_t launch_bwd_ring(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx,
+                                   float* dw_partial, int64_t rows, int cols, int g, cudaStream_t st) {
+    const BwdCfg c = bwd_cfg(cols, ADD);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rmsnorm_bwd_ring_kernel<THREADS, ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    rmsnorm_bwd_ring_kernel<THREADS, ADD><<<g, THREADS, c.smem, st>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,
+        (__nv_bfloat16*)dx, dw_partial, rows, cols, c.stages);
+    return cudaGetLastError();
+}
+
+template <bool ADD>
+static cudaError_t launch_bwd_ring_any(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
+                                       void* dx, float* dw_partial, int64_t rows, int cols, int g, cudaStream_t st) {
+    switch (bwd_cfg(cols, ADD).threads) {
+        case 128: return launch_bwd_ring<128, ADD>(dy, x, w, rstd, dres, dx, dw_partial, rows, cols, g, st);
+        case 256: return launch_bwd_ring<256, ADD>(dy, x, w, rstd, dres, dx, dw_partial, rows, cols, g, st);
+        case 512: return launch_bwd_ring<512, ADD>(dy, x, w, rstd, dres, dx, dw_partial, rows, cols, g, st);
+        default: return launch_bwd_ring<1024, ADD>(dy, x, w, rstd, dres, dx, dw_partial, rows, cols, g, st);
+    }
 }
 
 }  // namespace vb
@@ -522,22 +681,17 @@ extern "C" int vb200_rmsnorm_bwd(const void* dy, const void* x, const void* w, c
                         *w_ = (const __nv_bfloat16*)w;
     __nv_bfloat16* dx_ = (__nv_bfloat16*)dx;
 #define SMALL(T) rmsnorm_bwd_small_kernel<T><<<g, 256, 0, st>>>(dy_, x_, w_, rstd, dx_, dw_partial, rows, (int)cols)
-#define WIDE(T, V) rmsnorm_bwd_wide_kernel<T, V><<<g, T, 0, st>>>(dy_, x_, w_, rstd, dx_, dw_partial, rows, (int)cols)
     if (nvec <= 1) SMALL(1);
     else if (nvec <= 2) SMALL(2);
     else if (nvec <= 4) SMALL(4);
     else if (nvec <= 8) SMALL(8);
     else if (nvec <= 16) SMALL(16);
     else if (nvec <= 32) SMALL(32);
-    else if (nvec <= 128) WIDE(128, 1);
-    else if (nvec <= 256) WIDE(256, 1);
-    else if (nvec <= 512) WIDE(512, 1);
-    else if (nvec <= 1024) WIDE(512, 2);
-    else WIDE(512, 4);
+    else if (nvec <= 1024) VB_CUDA_TRY(launch_bwd_ring_any<false>(dy, x, w, rstd, nullptr, dx, dw_partial, rows, (int)cols, g, st));
+    else rmsnorm_bwd_wide_kernel<512, 4><<<g, 512, 0, st>>>(dy_, x_, w_, rstd, dx_, dw_partial, rows, (int)cols);
 #undef SMALL
-#undef WIDE
     VB_HOST_CHECK_LAUNCH();
-    colsum_kernel<<<(int)((cols + 31) / 32), 256, 0, st>>>(dw_partial, dw, g, (int)cols);
+    VB_CUDA_TRY(launch_colsum(dw_partial, dw, g, (int)cols, st));
     vb200_count_launch(2);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
@@ -580,18 +734,14 @@ extern "C" int vb200_rmsnorm_bwd_add(const void* dy, const void* x, const void* 
     }
     const int nvec = (int)(cols >> 3);
     const int g = bwd_grid(rows, (int)cols);
-#define WIDE(T, V)                                                                                                         \
-    rmsnorm_bwd_wide_add_kernel<T, V><<<g, T, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,                   \
-                                                       (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,           \
-                                                       (__nv_bfloat16*)dx, dw_partial, rows, (int)cols)
-    if (nvec <= 128) WIDE(128, 1);
-    else if (nvec <= 256) WIDE(256, 1);
-    else if (nvec <= 512) WIDE(512, 1);
-    else if (nvec <= 1024) WIDE(512, 2);
-    else WIDE(512, 4);
-#undef WIDE
+    if (nvec <= 1024)
+        VB_CUDA_TRY(launch_bwd_ring_any<true>(dy, x, w, rstd, dres, dx, dw_partial, rows, (int)cols, g, st));
+    else
+        rmsnorm_bwd_wide_add_kernel<512, 4><<<g, 512, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                             (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,
+                                                             (__nv_bfloat16*)dx, dw_partial, rows, (int)cols);
     VB_HOST_CHECK_LAUNCH();
-    colsum_kernel<<<(int)((cols + 31) / 32), 256, 0, st>>>(dw_partial, dw, g, (int)cols);
+    VB_CUDA_TRY(launch_colsum(dw_partial, dw, g, (int)cols, st));
     vb200_count_launch(2);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;

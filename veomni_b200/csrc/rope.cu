@@ -24,36 +24,48 @@ namespace vb {
 constexpr int kHeadChunk = 2;  // heads per work item
 constexpr int kSub = 2;        // heads in flight per thread (all of an item: 8 x 16 B loads + the 4 table loads)
 
+// cos/sin of one token for this lane's 8 + 8 columns, as packed fp32 pairs (the arithmetic below is FMUL2 / FFMA2: one issue
+// slot per two elements). ns_lo = -sin_lo, so both rotations are a multiply feeding a fused multiply-add.
 struct RopeTables {
-    float c_lo[8], c_hi[8], s_lo[8], s_hi[8];
+    float2 c_lo[4], c_hi[4], s_hi[4], ns_lo[4];
 };
+
+__device__ __forceinline__ void unpack4(const uint4& u, float2 (&f)[4]) {
+    f[0] = bf2_to_f2(u.x); f[1] = bf2_to_f2(u.y); f[2] = bf2_to_f2(u.z); f[3] = bf2_to_f2(u.w);
+}
+__device__ __forceinline__ uint4 pack4(const float2 (&f)[4]) {
+    return make_uint4(f2_to_bf2(f[0].x, f[0].y), f2_to_bf2(f[1].x, f[1].y), f2_to_bf2(f[2].x, f[2].y), f2_to_bf2(f[3].x, f[3].y));
+}
 
 __device__ __forceinline__ void load_tables(RopeTables& t, const __nv_bfloat16* cos, const __nv_bfloat16* sin,
                                             int64_t tok, int D, int sub) {
     const int half = D >> 1;
-    unpack8(*reinterpret_cast<const uint4*>(cos + tok * D + sub * 8), t.c_lo);
-    unpack8(*reinterpret_cast<const uint4*>(cos + tok * D + half + sub * 8), t.c_hi);
-    unpack8(*reinterpret_cast<const uint4*>(sin + tok * D + sub * 8), t.s_lo);
-    unpack8(*reinterpret_cast<const uint4*>(sin + tok * D + half + sub * 8), t.s_hi);
+    float2 s_lo[4];
+    unpack4(*reinterpret_cast<const uint4*>(cos + tok * D + sub * 8), t.c_lo);
+    unpack4(*reinterpret_cast<const uint4*>(cos + tok * D + half + sub * 8), t.c_hi);
+    unpack4(*reinterpret_cast<const uint4*>(sin + tok * D + sub * 8), s_lo);
+    unpack4(*reinterpret_cast<const uint4*>(sin + tok * D + half + sub * 8), t.s_hi);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t.ns_lo[i] = make_float2(-s_lo[i].x, -s_lo[i].y);
 }
 
 // forward rotation:  o_lo = x_lo*c_lo - x_hi*s_lo ; o_hi = x_hi*c_hi + x_lo*s_hi
-__device__ __forceinline__ void rotate_fwd(const RopeTables& t, const float (&lo)[8], const float (&hi)[8],
-                                           float (&olo)[8], float (&ohi)[8]) {
+__device__ __forceinline__ void rotate_fwd(const RopeTables& t, const float2 (&lo)[4], const float2 (&hi)[4],
+                                           float2 (&olo)[4], float2 (&ohi)[4]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        olo[i] = lo[i] * t.c_lo[i] - hi[i] * t.s_lo[i];
-        ohi[i] = hi[i] * t.c_hi[i] + lo[i] * t.s_hi[i];
+    for (int i = 0; i < 4; ++i) {
+        olo[i] = ffma2(lo[i], t.c_lo[i], fmul2(hi[i], t.ns_lo[i]));
+        ohi[i] = ffma2(hi[i], t.c_hi[i], fmul2(lo[i], t.s_hi[i]));
     }
 }
 // transposed rotation (vector-Jacobian product of rotate_fwd):
 //   dx_lo = g_lo*c_lo + g_hi*s_hi ; dx_hi = g_hi*c_hi - g_lo*s_lo
-__device__ __forceinline__ void rotate_bwd(const RopeTables& t, const float (&glo)[8], const float (&ghi)[8],
-                                           float (&dlo)[8], float (&dhi)[8]) {
+__device__ __forceinline__ void rotate_bwd(const RopeTables& t, const float2 (&glo)[4], const float2 (&ghi)[4],
+                                           float2 (&dlo)[4], float2 (&dhi)[4]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        dlo[i] = glo[i] * t.c_lo[i] + ghi[i] * t.s_hi[i];
-        dhi[i] = ghi[i] * t.c_hi[i] - glo[i] * t.s_lo[i];
+    for (int i = 0; i < 4; ++i) {
+        dlo[i] = ffma2(glo[i], t.c_lo[i], fmul2(ghi[i], t.s_hi[i]));
+        dhi[i] = ffma2(ghi[i], t.c_hi[i], fmul2(glo[i], t.ns_lo[i]));
     }
 }
 
@@ -93,15 +105,15 @@ rope_kernel(const __nv_bfloat16* __restrict__ q_in, __nv_bfloat16* __restrict__ 
             for (int j = 0; j < kSub; ++j) {
                 const int h = h0 + jb + j;
                 if (h < H) {
-                    float lo[8], hi[8], olo[8], ohi[8];
-                    unpack8(lo_v[j], lo);
-                    unpack8(hi_v[j], hi);
+                    float2 lo[4], hi[4], olo[4], ohi[4];
+                    unpack4(lo_v[j], lo);
+                    unpack4(hi_v[j], hi);
                     if (inverse) rotate_bwd(t, lo, hi, olo, ohi);
                     else rotate_fwd(t, lo, hi, olo, ohi);
                     __nv_bfloat16* dst = h < Hq ? q_out + tok * qos_t + (int64_t)h * qos_h
                                                 : k_out + tok * kos_t + (int64_t)(h - Hq) * kos_h;
-                    stg_stream(dst + sub * 8, pack8(olo));
-                    stg_stream(dst + HALF + sub * 8, pack8(ohi));
+                    stg_stream(dst + sub * 8, pack4(olo));
+                    stg_stream(dst + HALF + sub * 8, pack4(ohi));
                 }
             }
         }
@@ -158,28 +170,34 @@ qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
                 const int h = h0 + jb + j;
                 const bool ok = item_ok && h < H;
                 const bool is_q = h < Hq;
-                float lo[8], hi[8];
-                unpack8(lo_v[j], lo);
-                unpack8(hi_v[j], hi);
-                float ss = 0.f;
+                float2 lo[4], hi[4];
+                unpack4(lo_v[j], lo);
+                unpack4(hi_v[j], hi);
+                float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ss = fmaf(lo[i], lo[i], fmaf(hi[i], hi[i], ss));
-                ss = group_sum<LPH>(ss);
+                for (int i = 0; i < 4; ++i) {
+                    a0 = ffma2(lo[i], lo[i], a0);
+                    a1 = ffma2(hi[i], hi[i], a1);
+                }
+                const float ss = group_sum<LPH>((a0.x + a0.y) + (a1.x + a1.y));
                 const float rs = rsqrtf(ss * inv_d + eps);
                 if (ok) {
-                    float olo[8], ohi[8], w_lo[8], w_hi[8];
-                    unpack8(is_q ? wq_lo_p : wk_lo_p, w_lo);
-                    unpack8(is_q ? wq_hi_p : wk_hi_p, w_hi);
+                    // y = bf16(w * bf16(x*rstd)): the reference materialises q_norm's output in bf16. The second product is a
+                    // packed bf16 multiply on the still-packed weights (exact product, one rounding).
+                    const float2 rs2 = make_float2(rs, rs);
+                    const uint4 wl = is_q ? wq_lo_p : wk_lo_p, wh = is_q ? wq_hi_p : wk_hi_p;
+                    const uint32_t wlu[4] = {wl.x, wl.y, wl.z, wl.w}, whu[4] = {wh.x, wh.y, wh.z, wh.w};
+                    float2 olo[4], ohi[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        // y = bf16(w * bf16(x*rstd)): the reference materialises q_norm's output in bf16
-                        lo[i] = round_bf16(w_lo[i] * round_bf16(lo[i] * rs));
-                        hi[i] = round_bf16(w_hi[i] * round_bf16(hi[i] * rs));
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 tl = fmul2(lo[i], rs2), th = fmul2(hi[i], rs2);
+                        lo[i] = bf2_to_f2(bf2_mul(wlu[i], f2_to_bf2(tl.x, tl.y)));
+                        hi[i] = bf2_to_f2(bf2_mul(whu[i], f2_to_bf2(th.x, th.y)));
                     }
                     rotate_fwd(t, lo, hi, olo, ohi);
                     __nv_bfloat16* dst = is_q ? q_out + (tok * Hq + h) * D : k_out + (tok * Hk + (h - Hq)) * D;
-                    stg_stream(dst + sub * 8, pack8(olo));
-                    stg_stream(dst + HALF + sub * 8, pack8(ohi));
+                    stg_stream(dst + sub * 8, pack4(olo));
+                    stg_stream(dst + HALF + sub * 8, pack4(ohi));
                     if (sub == 0) {
                         if (is_q) rstd_q[tok * Hq + h] = rs;
                         else rstd_k[tok * Hk + (h - Hq)] = rs;
@@ -210,8 +228,9 @@ qknorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq_out, const __nv_bflo
     const uint4 wq_hi_p = *reinterpret_cast<const uint4*>(wq + HALF + sub * 8);
     const uint4 wk_lo_p = *reinterpret_cast<const uint4*>(wk + sub * 8);
     const uint4 wk_hi_p = *reinterpret_cast<const uint4*>(wk + HALF + sub * 8);
-    float aq_lo[8] = {0, 0, 0, 0, 0, 0, 0, 0}, aq_hi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float ak_lo[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ak_hi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float2 aq_lo[4], aq_hi[4], ak_lo[4], ak_hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) aq_lo[i] = aq_hi[i] = ak_lo[i] = ak_hi[i] = make_float2(0.f, 0.f);
     const int64_t per_iter = (int64_t)gridDim.x * GROUPS;
     const int64_t first = (int64_t)blockIdx.x * GROUPS + grp;
     const int64_t padded = (items + per_iter - 1) / per_iter * per_iter;
@@ -220,9 +239,8 @@ qknorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq_out, const __nv_bflo
         const bool item_ok = item < items;
         const int64_t tok = item_ok ? item / nchunks : 0;
         const int h0 = item_ok ? (int)(item % nchunks) * kHeadChunk : 0;
-        // cos/sin stay packed (bf16x8) until used: the unpacked tables would cost 32 registers next to the 32 dw accumulators
-        const uint4 tcl = *reinterpret_cast<const uint4*>(cos + tok * D + sub * 8), tch = *reinterpret_cast<const uint4*>(cos + tok * D + HALF + sub * 8);
-        const uint4 tsl = *reinterpret_cast<const uint4*>(sin + tok * D + sub * 8), tsh = *reinterpret_cast<const uint4*>(sin + tok * D + HALF + sub * 8);
+        RopeTables t;
+        load_tables(t, cos, sin, tok, D, sub);
         // all loads of the item first (8 x 16 B in flight per thread), then the arithmetic
         uint4 gv[kHeadChunk][2], xv[kHeadChunk][2];
         float rsv[kHeadChunk];
@@ -249,59 +267,60 @@ qknorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq_out, const __nv_bflo
             const bool ok = item_ok && h < H;
             const bool is_q = h < Hq;
             const int64_t row = is_q ? (tok * Hq + h) : (tok * Hk + (h - Hq));
-            float glo[8], ghi[8], xlo[8], xhi[8];
-            unpack8(gv[j][0], glo);
-            unpack8(gv[j][1], ghi);
-            unpack8(xv[j][0], xlo);
-            unpack8(xv[j][1], xhi);
+            // Operands are unpacked pair by pair so that only xhat and g (= dy * w) stay live across the row reduction.
+            float2 xlo[4], xhi[4], dlo[4], dhi[4];
             const float rs = rsv[j];
-            float dlo[8], dhi[8];
-            {
-                RopeTables t;
-                unpack8(tcl, t.c_lo); unpack8(tch, t.c_hi); unpack8(tsl, t.s_lo); unpack8(tsh, t.s_hi);
-                rotate_bwd(t, glo, ghi, dlo, dhi);  // dy of the norm
-            }
-            float dot = 0.f, w_lo[8], w_hi[8];
-            unpack8(is_q ? wq_lo_p : wk_lo_p, w_lo);
-            unpack8(is_q ? wq_hi_p : wk_hi_p, w_hi);
+            const float2 rs2 = make_float2(rs, rs);
+            const uint4 wl = is_q ? wq_lo_p : wk_lo_p, wh = is_q ? wq_hi_p : wk_hi_p;
+            const uint32_t glu[4] = {gv[j][0].x, gv[j][0].y, gv[j][0].z, gv[j][0].w}, ghu[4] = {gv[j][1].x, gv[j][1].y, gv[j][1].z, gv[j][1].w};
+            const uint32_t xlu[4] = {xv[j][0].x, xv[j][0].y, xv[j][0].z, xv[j][0].w}, xhu[4] = {xv[j][1].x, xv[j][1].y, xv[j][1].z, xv[j][1].w};
+            const uint32_t wlu[4] = {wl.x, wl.y, wl.z, wl.w}, whu[4] = {wh.x, wh.y, wh.z, wh.w};
+            float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float wl = w_lo[i], wh = w_hi[i];
-                xlo[i] *= rs;  // xhat
-                xhi[i] *= rs;
-                const float rl = round_bf16(xlo[i]), rh = round_bf16(xhi[i]);
+            for (int i = 0; i < 4; ++i) {
+                const float2 gl = bf2_to_f2(glu[i]), gh = bf2_to_f2(ghu[i]);
+                // transposed rotation (dy of the norm): dlo = g_lo*c_lo + g_hi*s_hi ; dhi = g_hi*c_hi - g_lo*s_lo
+                const float2 dyl = ffma2(gl, t.c_lo[i], fmul2(gh, t.s_hi[i])), dyh = ffma2(gh, t.c_hi[i], fmul2(gl, t.ns_lo[i]));
+                xlo[i] = fmul2(bf2_to_f2(xlu[i]), rs2);  // xhat
+                xhi[i] = fmul2(bf2_to_f2(xhu[i]), rs2);
+                const float2 rl = bf2_to_f2(f2_to_bf2(xlo[i].x, xlo[i].y)), rh = bf2_to_f2(f2_to_bf2(xhi[i].x, xhi[i].y));
                 if (is_q) {
-                    aq_lo[i] = fmaf(dlo[i], rl, aq_lo[i]);
-                    aq_hi[i] = fmaf(dhi[i], rh, aq_hi[i]);
+                    aq_lo[i] = ffma2(dyl, rl, aq_lo[i]);
+                    aq_hi[i] = ffma2(dyh, rh, aq_hi[i]);
                 } else {
-                    ak_lo[i] = fmaf(dlo[i], rl, ak_lo[i]);
-                    ak_hi[i] = fmaf(dhi[i], rh, ak_hi[i]);
+                    ak_lo[i] = ffma2(dyl, rl, ak_lo[i]);
+                    ak_hi[i] = ffma2(dyh, rh, ak_hi[i]);
                 }
-                dlo[i] *= wl;  // g = dy * w
-                dhi[i] *= wh;
-                dot = fmaf(dlo[i], xlo[i], fmaf(dhi[i], xhi[i], dot));
+                dlo[i] = fmul2(dyl, bf2_to_f2(wlu[i]));  // g = dy * w
+                dhi[i] = fmul2(dyh, bf2_to_f2(whu[i]));
+                dot2 = ffma2(dlo[i], xlo[i], ffma2(dhi[i], xhi[i], dot2));
             }
-            dot = group_sum<LPH>(dot);
-            const float c = dot * inv_d;
+            const float dot = group_sum<LPH>(dot2.x + dot2.y);
             if (ok) {
-                float olo[8], ohi[8];
+                const float nc = -dot * inv_d;
+                const float2 nc2 = make_float2(nc, nc);
+                float2 olo[4], ohi[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    olo[i] = rs * (dlo[i] - xlo[i] * c);
-                    ohi[i] = rs * (dhi[i] - xhi[i] * c);
+                for (int i = 0; i < 4; ++i) {
+                    olo[i] = fmul2(rs2, ffma2(xlo[i], nc2, dlo[i]));  // rs * (g - xhat * c)
+                    ohi[i] = fmul2(rs2, ffma2(xhi[i], nc2, dhi[i]));
                 }
                 __nv_bfloat16* dst = (is_q ? dq_in : dk_in) + row * D;
-                stg_stream(dst + sub * 8, pack8(olo));
-                stg_stream(dst + HALF + sub * 8, pack8(ohi));
+                stg_stream(dst + sub * 8, pack4(olo));
+                stg_stream(dst + HALF + sub * 8, pack4(ohi));
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        acc_s[grp][sub * 8 + i] = aq_lo[i];
-        acc_s[grp][HALF + sub * 8 + i] = aq_hi[i];
-        acc_s[grp][D + sub * 8 + i] = ak_lo[i];
-        acc_s[grp][D + HALF + sub * 8 + i] = ak_hi[i];
+    for (int i = 0; i < 4; ++i) {
+        acc_s[grp][sub * 8 + 2 * i] = aq_lo[i].x;
+        acc_s[grp][sub * 8 + 2 * i + 1] = aq_lo[i].y;
+        acc_s[grp][HALF + sub * 8 + 2 * i] = aq_hi[i].x;
+        acc_s[grp][HALF + sub * 8 + 2 * i + 1] = aq_hi[i].y;
+        acc_s[grp][D + sub * 8 + 2 * i] = ak_lo[i].x;
+        acc_s[grp][D + sub * 8 + 2 * i + 1] = ak_lo[i].y;
+        acc_s[grp][D + HALF + sub * 8 + 2 * i] = ak_hi[i].x;
+        acc_s[grp][D + HALF + sub * 8 + 2 * i + 1] = ak_hi[i].y;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < 2 * D; c += 256) {
@@ -319,6 +338,7 @@ colsum2_kernel(const float* __restrict__ partial, float* __restrict__ out_a, flo
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
     float t = 0.f;
+    griddep_wait();  // launched with programmatic stream serialization right behind qknorm_rope_bwd_kernel
     if (c < 2 * D)
         for (int64_t p = y; p < nparts; p += 8) t += partial[p * 2 * D + c];
     red[y][x] = t;
@@ -428,7 +448,18 @@ extern "C" int vb200_qknorm_rope_bwd(const void* dq_out, const void* dk_out, con
     else GO(16);
 #undef GO
     VB_HOST_CHECK_LAUNCH();
-    colsum2_kernel<<<(2 * head_dim + 31) / 32, 256, 0, st>>>(dw_partial, dwq, dwk, g, head_dim);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((2 * head_dim + 31) / 32));
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, colsum2_kernel, (const float*)dw_partial, dwq, dwk, (int64_t)g, (int)head_dim));
+    }
     vb200_count_launch(2);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;

@@ -148,7 +148,16 @@ def plan_chunks(counts: torch.Tensor, r: int, row: int):
     return input_splits, output_splits, total_recv, cumsum_host, fwd.contiguous(), bwd.contiguous()
 
 
+def _staged(c: "EPContext", tag: str, rows: int, H: int):
+    """(staging buffer, its [rows, H] bf16 view). The buffer itself is what a collective publishes: a rank that received no
+    token at all (``rows == 0``: routing collapse, tiny batches) still takes part in the exchange, and an empty view has no
+    address to derive the offset from."""
+    buf = c.staging(tag, max(rows, 1) * H * 2)
+    return buf, buf.view(BF)[: rows * H].view(-1, H)
+
+
 def _pull(ctx: EPContext, channel: int, src_buf: torch.Tensor, chunks: torch.Tensor, n: int, out: torch.Tensor) -> None:
+    """``src_buf`` = this rank's staging buffer (never empty); ``out`` may be empty."""
     lib = _lib.load()
     with torch.cuda.device(out.device), prof.span("ep_pull", out.numel() * out.element_size() * (ctx.ep_size - 1) / ctx.ep_size):
         check(lib.vb200_chunk_pull(ctx.symm.comm, channel, ctx.symm.offset_of(src_buf), chunks.data_ptr(), n,
@@ -170,10 +179,10 @@ class _EPDispatch(torch.autograd.Function):
     @staticmethod
     def forward(ctx, hs, plan: EPPlan):
         c = plan.ctx
-        send = c.staging("dispatch_send", plan.T * plan.K * plan.H * 2).view(BF)[: plan.T * plan.K * plan.H].view(-1, plan.H)
+        sbuf, send = _staged(c, "dispatch_send", plan.T * plan.K, plan.H)
         _scatter_into(hs.contiguous(), plan.sidx, send)
         recv = torch.empty(max(plan.total_recv, 1), plan.H, dtype=BF, device=hs.device)[: plan.total_recv]
-        _pull(c, CH_EP_DISPATCH, send, plan.fwd_chunks, plan.n_fwd, recv)
+        _pull(c, CH_EP_DISPATCH, sbuf, plan.fwd_chunks, plan.n_fwd, recv)
         ctx.plan = plan
         return recv
 
@@ -182,10 +191,10 @@ class _EPDispatch(torch.autograd.Function):
         plan: EPPlan = ctx.plan
         c = plan.ctx
         # gradients of received rows go back to their sources, then sum over the top-k slots
-        ret = c.staging("dispatch_grad", max(plan.total_recv, 1) * plan.H * 2).view(BF)[: plan.total_recv * plan.H].view(-1, plan.H)
+        rbuf, ret = _staged(c, "dispatch_grad", plan.total_recv, plan.H)
         ret.copy_(g)
         back = torch.empty(plan.T * plan.K, plan.H, dtype=BF, device=g.device)
-        _pull(c, CH_EP_COMBINE, ret, plan.bwd_chunks, plan.n_bwd, back)
+        _pull(c, CH_EP_COMBINE, rbuf, plan.bwd_chunks, plan.n_bwd, back)
         return _gather_raw(back, plan.sidx), None
 
 
@@ -195,10 +204,10 @@ class _EPCombine(torch.autograd.Function):
     @staticmethod
     def forward(ctx, expert_out, weights, plan: EPPlan):
         c = plan.ctx
-        ret = c.staging("combine_ret", max(plan.total_recv, 1) * plan.H * 2).view(BF)[: plan.total_recv * plan.H].view(-1, plan.H)
+        rbuf, ret = _staged(c, "combine_ret", plan.total_recv, plan.H)
         ret.copy_(expert_out)
         back = torch.empty(plan.T * plan.K, plan.H, dtype=BF, device=expert_out.device)
-        _pull(c, CH_EP_COMBINE, ret, plan.bwd_chunks, plan.n_bwd, back)
+        _pull(c, CH_EP_COMBINE, rbuf, plan.bwd_chunks, plan.n_bwd, back)
         w = weights.to(BF).contiguous()
         out = _gather_raw(back, plan.sidx, w)
         ctx.plan = plan
@@ -213,10 +222,10 @@ class _EPCombine(torch.autograd.Function):
         back, w = ctx.saved_tensors
         g = g.contiguous()
         # d/d(expert_out): scatter w[t,k] * g[t] into the permuted order, owners pull their rows
-        send = c.staging("combine_grad", plan.T * plan.K * plan.H * 2).view(BF)[: plan.T * plan.K * plan.H].view(-1, plan.H)
+        sbuf, send = _staged(c, "combine_grad", plan.T * plan.K, plan.H)
         _scatter_into(g, plan.sidx, send, w)
         grad_expert = torch.empty(max(plan.total_recv, 1), plan.H, dtype=BF, device=g.device)[: plan.total_recv]
-        _pull(c, CH_EP_DISPATCH, send, plan.fwd_chunks, plan.n_fwd, grad_expert)
+        _pull(c, CH_EP_DISPATCH, sbuf, plan.fwd_chunks, plan.n_fwd, grad_expert)
         # d/d(weights)[t,k] = <g[t], back[sidx[t,k]]>
         rows = back[plan.sidx.flatten().long()].view(plan.T, plan.K, plan.H)
         grad_w = torch.einsum("th,tkh->tk", g.float(), rows.float()).to(ctx.w_dtype)
