@@ -18,6 +18,9 @@
 // Forward, narrow rows (cols <= 256, e.g. per-head q/k norm): a group of lanes per row.
 // Backward: threads own columns and walk over rows, so dw accumulates in registers; one
 // __syncthreads per row (double-buffered partials), deterministic two-pass dw reduction.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vb {
@@ -25,13 +28,12 @@ namespace vb {
 // ------------------------------------------------------------------------------------------
 // forward, bulk-async staged
 // ------------------------------------------------------------------------------------------
-constexpr int kFwdStages = 2;   // rows in flight per warp
-constexpr int kFwdMaxWarps = 12; // 12 warps x 2 stages x 8 KB (H = 4096) fills the SM's shared memory
+constexpr int kFwdMaxWarps = 12;  // 12 warps x 2 rows in flight x 8 KB (H = 4096) fills the SM's shared memory
 
 __global__ void __launch_bounds__(kFwdMaxWarps * 32, 1)
 rmsnorm_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                         __nv_bfloat16* __restrict__ y, float* __restrict__ rstd, int64_t rows, int cols,
-                        float eps, int warps_per_cta) {
+                        float eps, int warps_per_cta, int kFwdStages) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row_bytes = (uint32_t)cols * 2u;
@@ -64,17 +66,16 @@ rmsnorm_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
         }
     }
     const float inv_cols = 1.0f / (float)cols;
-    int it = 0;
+    int it = 0, s = 0;
+    uint32_t parity = 0;
     for (int64_t r = gw; r < rows; r += GW, ++it) {
-        const int s = it % kFwdStages;
-        const uint32_t parity = (uint32_t)(it / kFwdStages) & 1u;
         uint4* buf = reinterpret_cast<uint4*>(my_bufs + (size_t)s * row_bytes);
         // Refill the buffer stored one iteration ago BEFORE working on this row: the load of the next row then overlaps
         // this row's arithmetic (the store only has to have been read out of shared memory, which takes well under a
         // microsecond, not to have landed).
         if (lane == 0 && it >= 1) {
             bulk_wait_read<0>();
-            const int ps = (it + kFwdStages - 1) % kFwdStages;
+            const int ps = s == 0 ? kFwdStages - 1 : s - 1;
             const int64_t nr = r + (int64_t)(kFwdStages - 1) * GW;
             if (nr < rows) {
                 mbar_expect_tx(&my_bars[ps], row_bytes);
@@ -97,6 +98,7 @@ rmsnorm_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
             bulk_commit();
         }
         __syncwarp();
+        if (++s == kFwdStages) { s = 0; parity ^= 1u; }
     }
     if (lane == 0) bulk_wait_all<0>();
 }
@@ -541,11 +543,18 @@ static BwdCfg bwd_cfg(int cols, bool add) {
     const int nvec = cols >> 3;
     BwdCfg c;
     c.threads = nvec <= 128 ? 128 : nvec <= 256 ? 256 : nvec <= 512 ? 512 : 1024;
-    c.ctas_per_sm = 2048 / c.threads;
+    c.ctas_per_sm = 1024 / c.threads;  // 64 registers per thread: 1024 threads per SM
     if (c.ctas_per_sm > 8) c.ctas_per_sm = 8;
+    if (c.ctas_per_sm < 1) c.ctas_per_sm = 1;
+    static int max_stages = 0;
+    if (!max_stages) {
+        const char* e = getenv("VB200_RMS_BWD_STAGES");  // tuning override
+        max_stages = e ? atoi(e) : 6;
+        if (max_stages < 2 || max_stages > kBwdMaxStages) max_stages = 6;
+    }
     const size_t stage = (size_t)(add ? 3 : 2) * cols * 2;
     const int st = (int)((200 * 1024 / c.ctas_per_sm) / stage);
-    c.stages = st > 6 ? 6 : st < 2 ? 2 : st;
+    c.stages = st > max_stages ? max_stages : st < 2 ? 2 : st;
     c.smem = stage * c.stages;
     return c;
 }
@@ -640,10 +649,20 @@ extern "C" int vb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* r
         else launch_fwd_small<32>(x, w, y, rstd, rows, (int)cols, eps, st);
     } else {
         const size_t row_bytes = (size_t)cols * 2;
-        int warps = (int)((200 * 1024 - row_bytes) / (row_bytes * kFwdStages));
-        if (warps > kFwdMaxWarps) warps = kFwdMaxWarps;
+        // (warps per CTA, rows in flight per warp): tuned on 4096 x 4096 (tools/hbm_sweep.sh); VB200_RMS_FWD_CFG="warps,stages"
+        // overrides for tuning runs.
+        static int cfg_warps = 0, cfg_stages = 0;
+        if (!cfg_warps) {
+            int w_ = kFwdMaxWarps, s_ = 2;
+            if (const char* e = getenv("VB200_RMS_FWD_CFG")) sscanf(e, "%d,%d", &w_, &s_);
+            cfg_warps = w_ < 1 ? 1 : w_ > kFwdMaxWarps ? kFwdMaxWarps : w_;
+            cfg_stages = s_ < 2 ? 2 : s_ > 8 ? 8 : s_;
+        }
+        const int stages = cfg_stages;
+        int warps = (int)((200 * 1024 - row_bytes) / (row_bytes * stages));
+        if (warps > cfg_warps) warps = cfg_warps;
         if (warps < 1) return vb200_set_error(VB200_EINVAL, "rmsnorm_fwd: row too wide for smem staging");
-        const size_t smem = row_bytes * (1 + (size_t)warps * kFwdStages) + sizeof(uint64_t) * warps * kFwdStages;
+        const size_t smem = row_bytes * (1 + (size_t)warps * stages) + sizeof(uint64_t) * warps * stages;
         static bool attr_set = false;
         if (!attr_set) {
             VB_CUDA_TRY(cudaFuncSetAttribute(rmsnorm_fwd_bulk_kernel,
@@ -654,7 +673,7 @@ extern "C" int vb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* r
         if (g > kNumSMs) g = kNumSMs;
         rmsnorm_fwd_bulk_kernel<<<(int)g, warps * 32, smem, st>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, rstd, rows, (int)cols, eps,
-            warps);
+            warps, stages);
     }
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();

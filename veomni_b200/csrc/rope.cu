@@ -13,6 +13,9 @@
 // [sub*8, sub*8+8) and their rotation partners at [D/2 + sub*8, ...), so the rotate_half pairing
 // never leaves the thread. One work item = (token, chunk of 8 heads): cos/sin for the token are
 // loaded once into registers and reused for the 8 heads.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vb {
@@ -21,8 +24,7 @@ namespace vb {
 // 40-head problem is 2.16 items per lane group, i.e. a third pass that is 16 % full (72 % of the achievable rate; the
 // backward's capped grid did worse); 2-head items make it 8.65 -> 9 passes (96 %). cos/sin rows are re-read per item,
 // from L2 (1 MB in total).
-constexpr int kHeadChunk = 2;  // heads per work item
-constexpr int kSub = 2;        // heads in flight per thread (all of an item: 8 x 16 B loads + the 4 table loads)
+constexpr int kHeadChunk = 2;  // heads per work item (backward; the forward kernels take it as a template parameter)
 
 // cos/sin of one token for this lane's 8 + 8 columns, as packed fp32 pairs (the arithmetic below is FMUL2 / FFMA2: one issue
 // slot per two elements). ns_lo = -sin_lo, so both rotations are a multiply feeding a fused multiply-add.
@@ -69,7 +71,7 @@ __device__ __forceinline__ void rotate_bwd(const RopeTables& t, const float2 (&g
     }
 }
 
-template <int LPH>
+template <int LPH, int HC>
 __global__ void __launch_bounds__(256, 2)
 rope_kernel(const __nv_bfloat16* __restrict__ q_in, __nv_bfloat16* __restrict__ q_out,
             const __nv_bfloat16* __restrict__ k_in, __nv_bfloat16* __restrict__ k_out,
@@ -78,21 +80,21 @@ rope_kernel(const __nv_bfloat16* __restrict__ q_in, __nv_bfloat16* __restrict__ 
             int64_t qos_h, int64_t kos_t, int64_t kos_h, int inverse) {
     constexpr int D = LPH * 16, HALF = D / 2;
     const int H = Hq + Hk;
-    const int nchunks = (H + kHeadChunk - 1) / kHeadChunk;
+    const int nchunks = (H + HC - 1) / HC;
     const int64_t items = tokens * nchunks;
     const int sub = threadIdx.x % LPH;
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPH;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x / LPH;
     for (int64_t item = gid; item < items; item += gstride) {
         const int64_t tok = item / nchunks;
-        const int h0 = (int)(item % nchunks) * kHeadChunk;
+        const int h0 = (int)(item % nchunks) * HC;
         RopeTables t;
         load_tables(t, cos, sin, tok, D, sub);
 #pragma unroll 1
-        for (int jb = 0; jb < kHeadChunk; jb += kSub) {
-            uint4 lo_v[kSub], hi_v[kSub];
+        for (int jb = 0; jb < HC; jb += HC) {
+            uint4 lo_v[HC], hi_v[HC];
 #pragma unroll
-            for (int j = 0; j < kSub; ++j) {
+            for (int j = 0; j < HC; ++j) {
                 const int h = h0 + jb + j;
                 if (h < H) {
                     const __nv_bfloat16* src = h < Hq ? q_in + tok * qs_t + (int64_t)h * qs_h
@@ -102,7 +104,7 @@ rope_kernel(const __nv_bfloat16* __restrict__ q_in, __nv_bfloat16* __restrict__ 
                 }
             }
 #pragma unroll
-            for (int j = 0; j < kSub; ++j) {
+            for (int j = 0; j < HC; ++j) {
                 const int h = h0 + jb + j;
                 if (h < H) {
                     float2 lo[4], hi[4], olo[4], ohi[4];
@@ -121,7 +123,7 @@ rope_kernel(const __nv_bfloat16* __restrict__ q_in, __nv_bfloat16* __restrict__ 
 }
 
 // ---- fused q/k-norm + RoPE ---------------------------------------------------------------
-template <int LPH>
+template <int LPH, int HC>
 __global__ void __launch_bounds__(256, 2)
 qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat16* __restrict__ k_in,
                        const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
@@ -131,7 +133,7 @@ qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
                        float eps) {
     constexpr int D = LPH * 16, HALF = D / 2;
     const int H = Hq + Hk;
-    const int nchunks = (H + kHeadChunk - 1) / kHeadChunk;
+    const int nchunks = (H + HC - 1) / HC;
     const int64_t items = tokens * nchunks;
     const int sub = threadIdx.x % LPH;
     // weights stay packed (bf16x8) to keep the register budget at 2 CTAs/SM
@@ -146,14 +148,14 @@ qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
     for (int64_t item = first; item < padded; item += per_iter) {
         const bool item_ok = item < items;
         const int64_t tok = item_ok ? item / nchunks : 0;
-        const int h0 = item_ok ? (int)(item % nchunks) * kHeadChunk : 0;
+        const int h0 = item_ok ? (int)(item % nchunks) * HC : 0;
         RopeTables t;
         load_tables(t, cos, sin, tok, D, sub);
 #pragma unroll 1
-        for (int jb = 0; jb < kHeadChunk; jb += kSub) {
-            uint4 lo_v[kSub], hi_v[kSub];
+        for (int jb = 0; jb < HC; jb += HC) {
+            uint4 lo_v[HC], hi_v[HC];
 #pragma unroll
-            for (int j = 0; j < kSub; ++j) {
+            for (int j = 0; j < HC; ++j) {
                 const int h = h0 + jb + j;
                 if (item_ok && h < H) {
                     const __nv_bfloat16* src =
@@ -166,7 +168,7 @@ qknorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ q_in, const __nv_bfloat
                 }
             }
 #pragma unroll
-            for (int j = 0; j < kSub; ++j) {
+            for (int j = 0; j < HC; ++j) {
                 const int h = h0 + jb + j;
                 const bool ok = item_ok && h < H;
                 const bool is_q = h < Hq;
@@ -352,13 +354,30 @@ colsum2_kernel(const float* __restrict__ partial, float* __restrict__ out_a, flo
     }
 }
 
-static int items_grid(int64_t tokens, int H, int lph, int max_ctas) {
-    const int nchunks = (H + kHeadChunk - 1) / kHeadChunk;
+static int items_grid(int64_t tokens, int H, int lph, int64_t max_ctas, int hc = kHeadChunk) {
+    const int nchunks = (H + hc - 1) / hc;
     const int64_t items = tokens * nchunks;
     const int groups = 256 / lph;
     int64_t g = (items + groups - 1) / groups;
     if (g > max_ctas) g = max_ctas;
     return (int)(g < 1 ? 1 : g);
+}
+
+// Forward-side launch shape: heads per work item (2 or 4: 4 or 8 x 16-byte loads in flight per thread) and the grid cap in
+// CTAs per SM (0 = one CTA per 32 lane groups of work, no grid-stride loop). VB200_ROPE_CFG="heads,ctas_per_sm" overrides
+// the defaults for tuning runs (tools/hbm_sweep.sh).
+struct RopeCfg {
+    int hc, cps;
+};
+static RopeCfg rope_cfg() {
+    static RopeCfg c = {0, 0};
+    if (!c.hc) {
+        int hc = 2, cps = 2;
+        if (const char* e = getenv("VB200_ROPE_CFG")) sscanf(e, "%d,%d", &hc, &cps);
+        c.hc = hc == 4 ? 4 : 2;
+        c.cps = cps < 0 ? 2 : cps;
+    }
+    return c;
 }
 
 }  // namespace vb
@@ -376,16 +395,23 @@ extern "C" int vb200_rope(const void* q_in, void* q_out, const void* k_in, void*
     if (tokens <= 0 || q_heads + k_heads <= 0) return VB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int lph = head_dim / 16;
-    const int g = items_grid(tokens, q_heads + k_heads, lph, 2 * kNumSMs);
+    const RopeCfg rc = rope_cfg();
+    const int g = items_grid(tokens, q_heads + k_heads, lph, rc.cps ? (int64_t)rc.cps * kNumSMs : (int64_t)1 << 30, rc.hc);
 #define GO(L)                                                                                            \
-    rope_kernel<L><<<g, 256, 0, st>>>((const __nv_bfloat16*)q_in, (__nv_bfloat16*)q_out,                 \
-                                      (const __nv_bfloat16*)k_in, (__nv_bfloat16*)k_out,                 \
-                                      (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, tokens,      \
-                                      q_heads, k_heads, qs_t, qs_h, ks_t, ks_h, qos_t, qos_h, kos_t, kos_h, \
-                                      inverse)
+    do {                                                                                                 \
+        if (rc.hc == 4) GO2(L, 4);                                                                       \
+        else GO2(L, 2);                                                                                  \
+    } while (0)
+#define GO2(L, C)                                                                                        \
+    rope_kernel<L, C><<<g, 256, 0, st>>>((const __nv_bfloat16*)q_in, (__nv_bfloat16*)q_out,              \
+                                         (const __nv_bfloat16*)k_in, (__nv_bfloat16*)k_out,              \
+                                         (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, tokens,   \
+                                         q_heads, k_heads, qs_t, qs_h, ks_t, ks_h, qos_t, qos_h, kos_t, kos_h, \
+                                         inverse)
     if (lph == 4) GO(4);
     else if (lph == 8) GO(8);
     else GO(16);
+#undef GO2
 #undef GO
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
@@ -401,15 +427,22 @@ extern "C" int vb200_qknorm_rope_fwd(const void* q_in, const void* k_in, const v
     if (tokens <= 0) return VB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int lph = head_dim / 16;
-    const int g = items_grid(tokens, q_heads + k_heads, lph, 2 * kNumSMs);  // = the resident CTAs (launch bounds 256 x 2)
+    const RopeCfg rc = rope_cfg();
+    const int g = items_grid(tokens, q_heads + k_heads, lph, rc.cps ? (int64_t)rc.cps * kNumSMs : (int64_t)1 << 30, rc.hc);
 #define GO(L)                                                                                           \
-    qknorm_rope_fwd_kernel<L><<<g, 256, 0, st>>>(                                                       \
+    do {                                                                                                \
+        if (rc.hc == 4) GO2(L, 4);                                                                      \
+        else GO2(L, 2);                                                                                 \
+    } while (0)
+#define GO2(L, C)                                                                                       \
+    qknorm_rope_fwd_kernel<L, C><<<g, 256, 0, st>>>(                                                    \
         (const __nv_bfloat16*)q_in, (const __nv_bfloat16*)k_in, (const __nv_bfloat16*)wq,               \
         (const __nv_bfloat16*)wk, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin,                 \
         (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_out, rstd_q, rstd_k, tokens, q_heads, k_heads, eps)
     if (lph == 4) GO(4);
     else if (lph == 8) GO(8);
     else GO(16);
+#undef GO2
 #undef GO
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
