@@ -196,6 +196,19 @@ def check_ep_dispatch(symm: SymmetricMemory, dev) -> str:
     back = EP.ep_combine(tokens, w, plan)
     if not torch.equal(back, (hs.float() * K).to(BF)):
         _fail("EP combine round trip")
+    # routing collapse: every token picks rank 0's first two experts, so every other rank receives NO row and still has
+    # to take part in all four exchanges (forward and backward of dispatch and combine)
+    hs2 = hs.clone().requires_grad_(True)
+    idx0 = torch.tensor([0, 1], device=dev).expand(T, K).contiguous()
+    tok0, plan0 = EP.ep_dispatch(ctx, hs2, idx0, E)
+    if (rank == 0) != (tok0.shape[0] == world * T * K) or (rank != 0 and tok0.shape[0] != 0):
+        _fail("EP dispatch under routing collapse (row count)")
+    back0 = EP.ep_combine(tok0, w, plan0)
+    if not torch.equal(back0.detach(), (hs.float() * K).to(BF)):
+        _fail("EP combine round trip under routing collapse")
+    back0.float().sum().backward()
+    if not torch.equal(hs2.grad, torch.full_like(hs, float(K))):
+        _fail("EP backward under routing collapse")
     symm.check()
     return "bit-exact"
 
