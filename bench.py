@@ -322,7 +322,9 @@ def run_b200(args) -> None:
         dist.barrier()
 
     for i in range(args.warmup):
-        step(resident[i % nbuf], i)
+        wl_ = step(resident[i % nbuf], i)
+        if os.environ.get("VB200_BENCH_DEBUG"):  # untimed: one sync per warm-up step to see the loss of every rank
+            print(f"[rank {rank}] warm-up step {i}: loss {float(wl_.item()):.5f}", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
@@ -463,6 +465,14 @@ def run_b200(args) -> None:
                     ent["frac_of_900"] = round(st["rate"] / 1e9 / 900.0, 3)
                 comm[tag] = ent
             out["comm"] = comm
+        if ep > 1:
+            from veomni_b200 import moe as vmoe_
+
+            st = dict(vmoe_._ep_state().stats)
+            rows_sent = seq_len * cfg.num_experts_per_tok
+            out["ep_routing"] = {"exchanges": st["calls"], "rows_sent_per_exchange": rows_sent, "rows_received_min": st["min_recv"],
+                                 "rows_received_max": st["max_recv"],
+                                 "rows_received_mean": round(st["sum_recv"] / max(1, st["calls"]), 1), "rank": rank}
         if parity is not None:
             out["parity"] = parity
         if nccl_ab is not None:

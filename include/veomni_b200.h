@@ -289,6 +289,10 @@ int vb200_moe_scatter(const void* x, const int32_t* scatter_index, void* out, co
  * veomni/distributed/moe/moe_utils.py:44-72).                                                  */
 int vb200_moe_gather(const void* x, const int32_t* scatter_index, const void* weights, void* out, int64_t tokens,
                      int32_t topk, int64_t hidden, void* stream);
+/* out[t,k] = <g[t,:], x[scatter_index[t,k],:]> (fp32): gradient of the weighted combine with respect to the routing
+ * weights (autograd of veomni/distributed/moe/moe_utils.py:44-72, `unpermute` with `probs`). hidden: multiple of 256.   */
+int vb200_moe_weight_grad(const void* g, const void* x, const int32_t* scatter_index, float* out, int64_t tokens,
+                          int32_t topk, int64_t hidden, void* stream);
 
 /* ---- ragged MoE GroupGEMM (tcgen05 tensor cores) ------------------------------------------
  * Replaces group_gemm_same_nk / group_gemm_same_mn

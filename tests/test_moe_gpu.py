@@ -69,6 +69,23 @@ def test_scatter_gather_vs_oracle(cuda_dev, T, K, H):
     assert torch.equal(xg.grad.cpu(), o_moe.moe_gather(y, sidx.cpu()))
 
 
+@pytest.mark.parametrize("T,K,H", [(3, 2, 256), (257, 8, 2048), (1000, 6, 4096), (64, 2, 64)])
+def test_routing_weight_grad_vs_fp32_einsum(cuda_dev, T, K, H):
+    """d(loss)/d(routing weight) of the EP combine: <g[t], rows[sidx[t,k]]> in fp32 (H = 64 takes the torch expression)."""
+    from veomni_b200.ep import routing_weight_grad
+    from veomni_b200.moe import moe_route
+
+    gen = torch.Generator().manual_seed(T + H)
+    idx = _rand_idx(T, K, 32, T + 1)
+    _, _, sidx = moe_route(idx.to(cuda_dev), 32)
+    g = torch.randn(T, H, generator=gen).to(BF)
+    rows = torch.randn(T * K, H, generator=gen).to(BF)
+    got = routing_weight_grad(g.to(cuda_dev), rows.to(cuda_dev), sidx).cpu()
+    want = torch.einsum("th,tkh->tk", g.double(), rows[sidx.cpu().flatten().long()].view(T, K, H).double()).float()
+    assert got.dtype == torch.float32 and got.shape == (T, K)
+    torch.testing.assert_close(got, want, atol=1e-3 * H ** 0.5, rtol=1e-4)  # fp32 accumulation order only
+
+
 def _ragged(G, total, seed, empties=()):
     g = torch.Generator().manual_seed(seed)
     w = torch.rand(G, generator=g)

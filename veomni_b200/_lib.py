@@ -64,6 +64,7 @@ SIGNATURES = {
     "vb200_moe_route": (c_int, [_P, _I32, _I64, _I32, _P, _P, _P, _P, _P]),
     "vb200_moe_scatter": (c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I64, _P]),
     "vb200_moe_gather": (c_int, [_P, _P, _P, _P, _I64, _I32, _I64, _P]),
+    "vb200_moe_weight_grad": (c_int, [_P, _P, _P, _P, _I64, _I32, _I64, _P]),
     "vb200_group_gemm": (c_int, [_I32, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P]),
     "vb200_symm_alloc": (c_int, [ctypes.POINTER(_P), _I64]),
     "vb200_symm_free": (c_int, [_P]),

@@ -52,8 +52,10 @@ def _launch(logits, labels, ignore_index, loss_rows, lse, lse_given, grad, scale
 
 
 def valid_label_recip(labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
-    """Device tensor ``[1/count, count]`` of labels != ignore_index (count 0 gives inf: the mean of nothing is NaN,
-    as ``F.cross_entropy(reduction="mean")`` returns)."""
+    """Device tensor ``[1/count, count]`` of labels != ignore_index. With no valid label the factor is 0, so the loss and
+    its gradient are exactly 0 for that batch (csrc/cross_entropy.cu ``ce_valid_recip_kernel``) — NOT the NaN that
+    ``F.cross_entropy(reduction="mean")`` returns for an all-ignored batch: a fully masked micro-batch does not poison
+    the step. Callers that want the eager NaN can test ``out[1] == 0`` themselves."""
     out = torch.empty(2, dtype=torch.float32, device=labels.device)
     lab = labels.reshape(-1).contiguous()
     if not lab.is_cuda or lab.dtype != torch.int64:

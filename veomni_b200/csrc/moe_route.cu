@@ -151,6 +151,38 @@ moe_gather_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ i
     }
 }
 
+// grad_w[t,k] = <g[t,:], x[index[t,k],:]> in fp32 (backward of the weighted combine with respect to the routing weights,
+// veomni/distributed/moe/moe_utils.py:44-72). One warp per token: g[t] stays in registers for the K rows it is dotted with.
+template <int VPL>  // 16-byte vectors per lane: hidden = VPL * 256
+__global__ void __launch_bounds__(256)
+moe_weight_grad_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ x, const int* __restrict__ index,
+                       float* __restrict__ out, int64_t T, int K) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+    constexpr int H = VPL * 256;
+    for (int64_t t = warp; t < T; t += nwarps) {
+        uint4 gv[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) gv[i] = ldg_stream(g + t * H + (i * 32 + lane) * 8);
+        for (int k = 0; k < K; ++k) {
+            const __nv_bfloat16* row = x + (int64_t)index[t * K + k] * H;
+            uint4 xv[VPL];
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) xv[i] = ldg_stream(row + (i * 32 + lane) * 8);
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                acc = ffma2(bf2_to_f2(gv[i].x), bf2_to_f2(xv[i].x), acc);
+                acc = ffma2(bf2_to_f2(gv[i].y), bf2_to_f2(xv[i].y), acc);
+                acc = ffma2(bf2_to_f2(gv[i].z), bf2_to_f2(xv[i].z), acc);
+                acc = ffma2(bf2_to_f2(gv[i].w), bf2_to_f2(xv[i].w), acc);
+            }
+            const float d = warp_sum(acc.x + acc.y);
+            if (lane == 0) out[t * K + k] = d;
+        }
+    }
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -212,6 +244,38 @@ extern "C" int vb200_moe_gather(const void* x, const int32_t* scatter_index, con
     else if (topk <= 4) GO(4);
     else if (topk <= 8) GO(8);
     else GO(16);
+#undef GO
+    vb200_count_launch(1);
+    VB_HOST_CHECK_LAUNCH();
+    return VB200_OK;
+}
+
+extern "C" int vb200_moe_weight_grad(const void* g, const void* x, const int32_t* scatter_index, float* out, int64_t tokens,
+                                     int32_t topk, int64_t hidden, void* stream) {
+    if (hidden <= 0 || (hidden & 255) || hidden > 8192)
+        return vb200_set_error(VB200_EINVAL, "moe_weight_grad: hidden must be a multiple of 256 up to 8192");
+    if (topk < 1) return vb200_set_error(VB200_EINVAL, "moe_weight_grad: topk must be positive");
+    if (tokens <= 0) return VB200_OK;
+    const int64_t want = (tokens + 7) / 8;
+    const int grid = (int)(want < 8 * kNumSMs ? want : 8 * kNumSMs);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GO(V)                                                                                                            \
+    moe_weight_grad_kernel<V><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)x, scatter_index, out, \
+                                                    tokens, topk)
+    switch ((int)(hidden >> 8)) {
+        case 1: GO(1); break;
+        case 2: GO(2); break;
+        case 3: GO(3); break;
+        case 4: GO(4); break;
+        case 5: GO(5); break;
+        case 6: GO(6); break;
+        case 7: GO(7); break;
+        case 8: GO(8); break;
+        case 16: GO(16); break;
+        case 20: GO(20); break;
+        case 32: GO(32); break;
+        default: return vb200_set_error(VB200_EINVAL, "moe_weight_grad: unsupported hidden size");
+    }
 #undef GO
     vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();

@@ -239,7 +239,7 @@ rmsnorm_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
 // hidden_states` rounds it), y = bf16(w * bf16(h * rstd)) — one pass over x and residual instead of an elementwise add
 // kernel followed by the norm. One warp per row, the row's h kept packed in registers between the two sweeps;
 // H = NCH * 256 elements.
-template <int NCH>
+template <int NCH, bool ADD>
 __global__ void __launch_bounds__(256)
 add_rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                        const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ h_out, __nv_bfloat16* __restrict__ y,
@@ -253,16 +253,18 @@ add_rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
-            const uint4 a = ldg_stream(xr + (k * 32 + lane) * 8), b = ldg_stream(rr + (k * 32 + lane) * 8);
-            float2 t;
-            uint4 h;  // h = bf16(x + residual): fp32 add, one rounding (as torch adds two bf16 tensors)
-            t = fadd2(bf2_to_f2(a.x), bf2_to_f2(b.x)); h.x = f2_to_bf2(t.x, t.y);
-            t = fadd2(bf2_to_f2(a.y), bf2_to_f2(b.y)); h.y = f2_to_bf2(t.x, t.y);
-            t = fadd2(bf2_to_f2(a.z), bf2_to_f2(b.z)); h.z = f2_to_bf2(t.x, t.y);
-            t = fadd2(bf2_to_f2(a.w), bf2_to_f2(b.w)); h.w = f2_to_bf2(t.x, t.y);
+            uint4 h = ldg_stream(xr + (k * 32 + lane) * 8);
+            if (ADD) {  // h = bf16(x + residual): fp32 add, one rounding (as torch adds two bf16 tensors)
+                const uint4 a = h, b = ldg_stream(rr + (k * 32 + lane) * 8);
+                float2 t;
+                t = fadd2(bf2_to_f2(a.x), bf2_to_f2(b.x)); h.x = f2_to_bf2(t.x, t.y);
+                t = fadd2(bf2_to_f2(a.y), bf2_to_f2(b.y)); h.y = f2_to_bf2(t.x, t.y);
+                t = fadd2(bf2_to_f2(a.z), bf2_to_f2(b.z)); h.z = f2_to_bf2(t.x, t.y);
+                t = fadd2(bf2_to_f2(a.w), bf2_to_f2(b.w)); h.w = f2_to_bf2(t.x, t.y);
+                stg_stream(h_out + row * H + (k * 32 + lane) * 8, h);
+            }
             sumsq8(h, acc0, acc1);
             hv[k] = h;
-            stg_stream(h_out + row * H + (k * 32 + lane) * 8, h);
         }
         const float ss = warp_sum((acc0.x + acc0.y) + (acc1.x + acc1.y));
         const float rs = rsqrtf(ss * (1.0f / (float)H) + eps);
@@ -513,23 +515,33 @@ rmsnorm_bwd_small_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat
     }
 }
 
-// out[c] = sum_p partial[p][c].  Block (32 columns x 8 partial-lanes): coalesced 128-byte rows, 8 independent
-// accumulation chains per column, combined in a fixed order (deterministic).
-__global__ void __launch_bounds__(256)
+// out[c] = sum_p partial[p][c].  Block = 32 columns x 32 partial-lanes (1024 threads), grid = cols / 32: every thread sums
+// nparts / 32 rows with its loads issued eight at a time (the 256-thread version walked 37 dependent round trips and cost
+// 5.5 us per call — a fifth of the backward it follows), coalesced 128-byte rows, combined in a fixed order
+// (deterministic).
+__global__ void __launch_bounds__(1024)
 colsum_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t nparts, int cols) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
     float t = 0.f;
     griddep_wait();  // launched with programmatic stream serialization right behind the kernel that writes `partial`
     if (c < cols)
-        for (int64_t p = y; p < nparts; p += 8) t += partial[p * cols + c];
+        for (int64_t p = y; p < nparts; p += 256) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t q = p + 32 * j;
+                v[j] = q < nparts ? partial[q * cols + c] : 0.f;
+            }
+            t += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
     red[y][x] = t;
     __syncthreads();
     if (y == 0 && c < cols) {
         float a = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a += red[i][x];
+        for (int i = 0; i < 32; ++i) a += red[i][x];
         out[c] = a;
     }
 }
@@ -549,8 +561,8 @@ static BwdCfg bwd_cfg(int cols, bool add) {
     static int max_stages = 0;
     if (!max_stages) {
         const char* e = getenv("VB200_RMS_BWD_STAGES");  // tuning override
-        max_stages = e ? atoi(e) : 6;
-        if (max_stages < 2 || max_stages > kBwdMaxStages) max_stages = 6;
+        max_stages = e ? atoi(e) : 2;  // deeper rings measured slower on 4096 x 4096 (profiles/r02_hbm_sweep.txt)
+        if (max_stages < 2 || max_stages > kBwdMaxStages) max_stages = 2;
     }
     const size_t stage = (size_t)(add ? 3 : 2) * cols * 2;
     const int st = (int)((200 * 1024 / c.ctas_per_sm) / stage);
@@ -581,7 +593,7 @@ static int bwd_grid(int64_t rows, int cols) {
 static cudaError_t launch_colsum(const float* partial, float* out, int64_t nparts, int cols, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((cols + 31) / 32));
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(1024);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -647,6 +659,21 @@ extern "C" int vb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* r
         else if (nvec <= 8) launch_fwd_small<8>(x, w, y, rstd, rows, (int)cols, eps, st);
         else if (nvec <= 16) launch_fwd_small<16>(x, w, y, rstd, rows, (int)cols, eps, st);
         else launch_fwd_small<32>(x, w, y, rstd, rows, (int)cols, eps, st);
+    } else if ((cols == 1024 || cols == 2048 || cols == 4096 || cols == 5120) && !getenv("VB200_RMS_FWD_CFG")) {
+        // The decoder hidden sizes: a warp keeps its row packed in registers between the two sweeps (no shared-memory
+        // staging, no per-launch barrier set-up) — 16.6 -> see profiles/r02_microbench_hbm_final.jsonl at 4096 x 4096; the
+        // bulk-staged kernel below keeps the general widths.
+        int64_t blocks = (rows + 7) / 8;
+        if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+#define GO(N)                                                                                                          \
+    add_rmsnorm_fwd_kernel<N, false><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, nullptr,               \
+                                                                       (const __nv_bfloat16*)w, nullptr,               \
+                                                                       (__nv_bfloat16*)y, rstd, rows, eps)
+        if (cols == 1024) GO(4);
+        else if (cols == 2048) GO(8);
+        else if (cols == 4096) GO(16);
+        else GO(20);
+#undef GO
     } else {
         const size_t row_bytes = (size_t)cols * 2;
         // (warps per CTA, rows in flight per warp): tuned on 4096 x 4096 (tools/hbm_sweep.sh); VB200_RMS_FWD_CFG="warps,stages"
@@ -724,9 +751,9 @@ extern "C" int vb200_add_rmsnorm_fwd(const void* x, const void* residual, const 
     int64_t blocks = (rows + 7) / 8;
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
 #define GO(N)                                                                                                               \
-    add_rmsnorm_fwd_kernel<N><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual,     \
-                                                                (const __nv_bfloat16*)w, (__nv_bfloat16*)h_out,              \
-                                                                (__nv_bfloat16*)y, rstd, rows, eps)
+    add_rmsnorm_fwd_kernel<N, true><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, \
+                                                                      (const __nv_bfloat16*)w, (__nv_bfloat16*)h_out,         \
+                                                                      (__nv_bfloat16*)y, rstd, rows, eps)
     switch (cols) {
         case 1024: GO(4); break;
         case 2048: GO(8); break;

@@ -333,22 +333,30 @@ qknorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq_out, const __nv_bflo
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 colsum2_kernel(const float* __restrict__ partial, float* __restrict__ out_a, float* __restrict__ out_b, int64_t nparts,
                int D) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + x;
     float t = 0.f;
     griddep_wait();  // launched with programmatic stream serialization right behind qknorm_rope_bwd_kernel
     if (c < 2 * D)
-        for (int64_t p = y; p < nparts; p += 8) t += partial[p * 2 * D + c];
+        for (int64_t p = y; p < nparts; p += 256) {  // eight independent loads per round trip (see colsum_kernel)
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t q = p + 32 * j;
+                v[j] = q < nparts ? partial[q * 2 * D + c] : 0.f;
+            }
+            t += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
     red[y][x] = t;
     __syncthreads();
     if (y == 0 && c < 2 * D) {
         float a = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a += red[i][x];
+        for (int i = 0; i < 32; ++i) a += red[i][x];
         if (c < D) out_a[c] = a;
         else out_b[c - D] = a;
     }
@@ -372,9 +380,9 @@ struct RopeCfg {
 static RopeCfg rope_cfg() {
     static RopeCfg c = {0, 0};
     if (!c.hc) {
-        int hc = 2, cps = 2;
+        int hc = 4, cps = 2;  // 4 heads / item, 2 CTAs per SM: profiles/r02_hbm_sweep.txt
         if (const char* e = getenv("VB200_ROPE_CFG")) sscanf(e, "%d,%d", &hc, &cps);
-        c.hc = hc == 4 ? 4 : 2;
+        c.hc = hc == 2 ? 2 : 4;
         c.cps = cps < 0 ? 2 : cps;
     }
     return c;
@@ -484,7 +492,7 @@ extern "C" int vb200_qknorm_rope_bwd(const void* dq_out, const void* dk_out, con
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)((2 * head_dim + 31) / 32));
-        cfg.blockDim = dim3(256);
+        cfg.blockDim = dim3(1024);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

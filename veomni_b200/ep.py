@@ -50,6 +50,9 @@ class EPContext:
         self.rank = self.symm.rank
         self.num_ctas = num_ctas
         self._bufs: dict[str, torch.Tensor] = {}
+        # host-side routing statistics (rows this rank received per exchange): load imbalance is what sizes the staging
+        # buffers and the GroupGEMM tail, so the bench line reports it
+        self.stats = {"calls": 0, "min_recv": None, "max_recv": 0, "sum_recv": 0}
 
     def staging(self, tag: str, nbytes: int) -> torch.Tensor:
         """ONE persistent symmetric buffer per tag, grown geometrically: receive sizes depend on the routing and differ on
@@ -113,6 +116,11 @@ def make_plan(ctx: EPContext, selected_experts: torch.Tensor, num_experts: int, 
     counts = cbuf.view(ep, num_experts).to("cpu", non_blocking=False).to(torch.int64)  # the one host sync
     input_splits, output_splits, total_recv, cumsum_host, fwd, bwd = plan_chunks(counts, r, hidden * 2)
     cumsum_local = cumsum_host.to(torch.int32).to(dev, non_blocking=True)
+    st = ctx.stats
+    st["calls"] += 1
+    st["sum_recv"] += total_recv
+    st["max_recv"] = max(st["max_recv"], total_recv)
+    st["min_recv"] = total_recv if st["min_recv"] is None else min(st["min_recv"], total_recv)
     return EPPlan(ctx, T, K, hidden, sidx, counts, input_splits, output_splits, total_recv, cumsum_local,
                   fwd.to(dev, non_blocking=True), fwd.shape[0], bwd.to(dev, non_blocking=True), bwd.shape[0])
 
@@ -173,6 +181,21 @@ def _scatter_into(x: torch.Tensor, sidx: torch.Tensor, out: torch.Tensor, w: tor
                                     None, T, K, x.shape[-1], stream_ptr()), "vb200_moe_scatter")
 
 
+def routing_weight_grad(g: torch.Tensor, rows: torch.Tensor, sidx: torch.Tensor) -> torch.Tensor:
+    """fp32 ``[T, K]``: ``<g[t], rows[sidx[t,k]]>`` — d(loss)/d(routing weight) of the weighted combine. One kernel (a warp
+    per token keeps ``g[t]`` in registers for its K rows) instead of a gathered ``[T, K, H]`` copy, two fp32 casts and an
+    einsum; hidden sizes that are not a multiple of 256 (toy models) keep the torch expression."""
+    T, K = sidx.shape
+    H = g.shape[-1]
+    if H % 256 or H > 8192 or (H // 256 > 8 and H // 256 not in (16, 20, 32)):
+        return torch.einsum("th,tkh->tk", g.float(), rows[sidx.flatten().long()].view(T, K, H).float())
+    out = torch.empty(T, K, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        check(_lib.load().vb200_moe_weight_grad(g.data_ptr(), rows.data_ptr(), sidx.data_ptr(), out.data_ptr(), T, K, H,
+                                                stream_ptr()), "vb200_moe_weight_grad")
+    return out
+
+
 class _EPDispatch(torch.autograd.Function):
     """token_pre_all2all (moe_layer.py:72-99): local permute -> exchange -> group by local expert."""
 
@@ -227,8 +250,7 @@ class _EPCombine(torch.autograd.Function):
         grad_expert = torch.empty(max(plan.total_recv, 1), plan.H, dtype=BF, device=g.device)[: plan.total_recv]
         _pull(c, CH_EP_DISPATCH, sbuf, plan.fwd_chunks, plan.n_fwd, grad_expert)
         # d/d(weights)[t,k] = <g[t], back[sidx[t,k]]>
-        rows = back[plan.sidx.flatten().long()].view(plan.T, plan.K, plan.H)
-        grad_w = torch.einsum("th,tkh->tk", g.float(), rows.float()).to(ctx.w_dtype)
+        grad_w = routing_weight_grad(g, back, plan.sidx).to(ctx.w_dtype)
         return grad_expert, grad_w, None
 
 
