@@ -96,6 +96,24 @@ def bench_rmsnorm(dev, iters):
                                   part.data_ptr(), dw.data_ptr(), T, H, st)
 
     report("rmsnorm_bwd_add[4096x4096]", time_fn(abwd, asets, iters), nbytes=4 * T * H * 2)
+    # the same kernels on 4x the rows (the Ulysses-32k per-rank shape x2): the 4096-row launches are 10 us of streaming plus
+    # ~6 us of launch ramp and drain, so the fraction at this size says how much of the gap is fixed cost
+    T4 = 4 * T
+    big = [(torch.randn(T4, H, device=dev, dtype=BF), torch.empty(T4, H, device=dev, dtype=BF),
+            torch.empty(T4, device=dev, dtype=torch.float32), torch.empty(T4, H, device=dev, dtype=BF)) for _ in range(2)]
+
+    def fwd4(x, y, r, _d):
+        lib.vb200_rmsnorm_fwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), r.data_ptr(), T4, H, 1e-6, st)
+
+    report("rmsnorm_fwd[16384x4096]", time_fn(fwd4, big, iters), nbytes=2 * T4 * H * 2)
+    part4 = torch.empty(lib.vb200_rmsnorm_bwd_partials(T4, H), H, device=dev, dtype=torch.float32)
+
+    def bwd4(x, dy, r, dx):
+        lib.vb200_rmsnorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), r.data_ptr(), dx.data_ptr(), part4.data_ptr(),
+                              dw.data_ptr(), T4, H, st)
+
+    report("rmsnorm_bwd[16384x4096]", time_fn(bwd4, big, iters), nbytes=3 * T4 * H * 2)
+    del big
     # per-head norm shape (q heads)
     R, C = 4096 * 40, 128
     hs = [(torch.randn(R, C, device=dev, dtype=BF), torch.empty(R, C, device=dev, dtype=BF),
