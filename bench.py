@@ -389,6 +389,12 @@ def run_b200(args) -> None:
         if rank == 0:
             with open(args.torch_profile, "w") as fh:
                 fh.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=70, max_name_column_width=90))
+                try:  # where the step idles: per-stream busy time and the compute stream's gaps (tools/stream_gaps.py)
+                    from tools import stream_gaps
+
+                    fh.write("\n" + stream_gaps.report(tp))
+                except Exception as ex:  # noqa: BLE001
+                    fh.write(f"\nstream_gaps failed: {type(ex).__name__}: {ex}\n")
         dist.barrier()
 
     if rank == 0:

@@ -110,6 +110,18 @@ __device__ __forceinline__ void finish_epoch(const CommDev& c, int ch, uint32_t 
     }
 }
 
+// One warp that performs the flag exchange a collective starts with (optionally sending this rank's flag first) and exits.
+// Launched in front of a many-CTA collective kernel on the same stream: the kernel then finds every peer ready and holds
+// its SMs only for the transfer, instead of parking 16-32 SMs' worth of CTAs in a spin loop until the slowest peer has
+// reached the same point of its step (1.2 ms of the 1.85 ms an in-step all-gather launch took at N=8 was that wait, with
+// the GEMMs next to it running on 116 SMs). The kernel repeats the exchange — same epoch, same values: idempotent.
+__global__ void __launch_bounds__(32)
+comm_gate_kernel(CommDev c, int ch, int kind, int64_t off, int do_signal) {
+    const uint32_t e = c.state[ch] + 1;
+    if (do_signal) signal_peers(c, ch, kind, e, off);
+    wait_peers(c, ch, kind, e);
+}
+
 // Copy `bytes` from src to dst (same alignment modulo 16) with the whole grid; 2-byte granularity.
 __device__ __forceinline__ void grid_copy(uint8_t* dst, const uint8_t* src, int64_t bytes) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -638,7 +650,9 @@ __device__ __forceinline__ uint4 ldg_cg_v4(const void* p) {  // L2-coherent load
 
 template <int W>
 __global__ void __launch_bounds__(512)
-reduce_scatter_push_bf16_kernel(CommDev c, int ch, int64_t off, PushArgs a, float scale, float* __restrict__ out) {
+reduce_scatter_push_bf16_kernel(CommDev c, int ch, int64_t off, PushArgs a, float scale, float* __restrict__ out, int phase) {
+    // phase 3: the whole collective in one launch. phase 1 (push) + phase 2 (reduce) as two launches with a gate kernel
+    // between them: the wait for the slowest peer's pushes then costs one warp instead of the whole grid.
     __shared__ int64_t peer_off[kMaxWorld];
     __shared__ int64_t s_prefix[kPushMax + 1];  // element offset of parameter i inside a row
     __shared__ const __nv_bfloat16* s_src[kPushMax];
@@ -646,6 +660,10 @@ reduce_scatter_push_bf16_kernel(CommDev c, int ch, int64_t off, PushArgs a, floa
     __shared__ int s_tprefix[kPushMax + 1];  // 64 KB tiles before parameter i inside one row
     __shared__ int s_last;
     const uint32_t e = c.state[ch] + 1;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
+    const int64_t row = a.row;
+    if (phase & 1) {
     if (blockIdx.x == 0) signal_peers(c, ch, 0, e, off);  // "my staging buffer (at off) is free for epoch e"
     if (threadIdx.x == 0) {
         int64_t acc = 0;
@@ -666,9 +684,6 @@ reduce_scatter_push_bf16_kernel(CommDev c, int ch, int64_t off, PushArgs a, floa
         s_chunk[i] = a.chunk[i];
     }
     wait_peers(c, ch, 0, e, peer_off);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthr = (int64_t)gridDim.x * blockDim.x;
-    const int64_t row = a.row;
     // ---- phase A: push -------------------------------------------------------------------------------------------
     // Work = (peer q, 64 KB tile of one parameter's chunk), walked like the all-gather's tiles: no per-vector search.
     if (a.vec_ok) {
@@ -732,7 +747,10 @@ reduce_scatter_push_bf16_kernel(CommDev c, int ch, int64_t off, PushArgs a, floa
     if (s_last) {
         __threadfence_system();
         signal_peers(c, ch, 1, e);  // "everything I owe you for epoch e has been written"
+        if (phase == 1 && threadIdx.x == 0) c.state[kMaxChannels + ch] = 0;  // every CTA has counted itself already
     }
+    }  // phase & 1
+    if (!(phase & 2)) return;
     wait_peers(c, ch, 1, e);
     // ---- phase B: reduce the world slots of the local staging buffer in rank order -------------------------------
     const __nv_bfloat16* stage = reinterpret_cast<const __nv_bfloat16*>(c.data[c.rank] + off);
@@ -882,6 +900,14 @@ static bool comm_cluster_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("VB200_COMM_CLUSTER");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+static bool comm_gate_enabled() {  // VB200_COMM_GATE=0: no gate kernels (the collectives spin on all their CTAs; A-B runs)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VB200_COMM_GATE");
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v != 0;
@@ -1037,8 +1063,10 @@ extern "C" int vb200_allgather_scatter(void* comm, int32_t channel, int64_t regi
         cfg.numAttrs = 1;
     }
     cfg.gridDim = dim3(ctas);
+    const bool gate = comm_gate_enabled() && h->dev.world > 1;
+    if (gate) comm_gate_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->dev, (int)channel, 0, region_offset, 1);
     VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, allgather_scatter_kernel, h->dev, (int)channel, region_offset, shard_bytes, a));
-    vb200_count_launch(1);
+    vb200_count_launch(gate ? 2 : 1);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
 }
@@ -1087,13 +1115,27 @@ extern "C" int vb200_reduce_scatter_push_bf16(void* comm, int32_t channel, int64
     cfg.gridDim = dim3(g);
     const char* gen = getenv("VB200_RS_GENERIC");
     const int ch32 = (int)channel;
-    switch ((gen && gen[0] == '1') ? 0 : h->dev.world) {
-        case 1: VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<1>, h->dev, ch32, region_offset, a, scale, out)); break;
-        case 2: VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<2>, h->dev, ch32, region_offset, a, scale, out)); break;
-        case 4: VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<4>, h->dev, ch32, region_offset, a, scale, out)); break;
-        default: VB_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<0>, h->dev, ch32, region_offset, a, scale, out)); break;
+    const int w = (gen && gen[0] == '1') ? 0 : h->dev.world;
+    const bool gate = comm_gate_enabled() && h->dev.world > 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto launch = [&](int phase) -> cudaError_t {
+        switch (w) {
+            case 1: return cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<1>, h->dev, ch32, region_offset, a, scale, out, phase);
+            case 2: return cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<2>, h->dev, ch32, region_offset, a, scale, out, phase);
+            case 4: return cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<4>, h->dev, ch32, region_offset, a, scale, out, phase);
+            default: return cudaLaunchKernelEx(&cfg, reduce_scatter_push_bf16_kernel<0>, h->dev, ch32, region_offset, a, scale, out, phase);
+        }
+    };
+    if (gate) {
+        comm_gate_kernel<<<1, 32, 0, st>>>(h->dev, ch32, 0, region_offset, 1);  // staging free on every peer
+        VB_CUDA_TRY(launch(1));                                                    // push
+        comm_gate_kernel<<<1, 32, 0, st>>>(h->dev, ch32, 1, region_offset, 0);  // every peer's pushes have landed here
+        VB_CUDA_TRY(launch(2));                                                    // local rank-order reduction
+        vb200_count_launch(4);
+    } else {
+        VB_CUDA_TRY(launch(3));
+        vb200_count_launch(1);
     }
-    vb200_count_launch(1);
     VB_HOST_CHECK_LAUNCH();
     return VB200_OK;
 }
