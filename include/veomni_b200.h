@@ -51,7 +51,7 @@ int vb200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int64_
  * workspace; dw: [cols] fp32 = column sums (deterministic two-pass reduction).            */
 int64_t vb200_rmsnorm_bwd_partials(int64_t rows, int64_t cols);
 /* Fused residual add + RMSNorm (the `hidden_states = residual + hidden_states` line before every
- * Qwen3RMSNorm in the decoder layer, patched_modeling_qwen3_gpu.py:369-375). EXPERIMENTAL until validated on hardware.
+ * Qwen3RMSNorm in the decoder layer, patched_modeling_qwen3_gpu.py:369-375).
  *   fwd: h_out = bf16(x + residual), y = RMSNorm(h_out) * w, rstd[rows];  cols in {1024, 2048, 4096, 5120, 8192}
  *   bwd: dx = rmsnorm_bwd(dy; x = h_out, w, rstd) + dres (bf16 sum), dw as vb200_rmsnorm_bwd; dres NULL = plain bwd */
 int vb200_add_rmsnorm_fwd(const void* x, const void* residual, const void* w, void* h_out, void* y, float* rstd,

@@ -21,6 +21,14 @@ def bench_attention(dev, iters):
                flops=flops_fwd)
     from veomni_b200 import attention as A
 
+    if os.environ.get("VB200_PROFILE_ONCE", "0") == "1":  # ncu capture run: the default kernels only, once each
+        gs = tuple(t.clone().requires_grad_(True) for t in sets[0])
+        do = torch.randn(T, Hq, D, device=dev, dtype=BF)
+        o = flash_attn_varlen(*gs, cu, T)
+        report("attn_bwd only (delta + dQ + dK/dV)[4096,32/8,128,causal]",
+               time_fn(lambda: o.backward(do, retain_graph=True), [()], iters), flops=flops_fwd * 2.5)
+        return
+
     old = A.FWD_IMPL
     A.FWD_IMPL = "tc"
     try:
@@ -91,7 +99,7 @@ def bench_attention(dev, iters):
                    flops=flops_fwd * 2.5)
         except Exception as ex:  # noqa: BLE001
             print({"attn_bwd_dq_n128": str(ex)})
-    A.BWD_DQ_N128 = False
+    A.BWD_DQ_N128 = True
     A.FWD_IMPL, A.BWD_IMPL = old2
     try:
         from flash_attn import flash_attn_varlen_func

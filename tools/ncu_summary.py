@@ -30,13 +30,12 @@ def main(path):
                 i = hdr.index(k)
                 print(f"  {k:75s} {r[i]:>16s} {units[i]}")
     stall = [h for h in hdr if h.startswith("smsp__pcsamp_warps_issue_stalled") and not h.endswith("_not_issued")]
-    if stall and len(rows) > 2:
-        r = rows[2]
-        vals = sorted(((float(r[hdr.index(h)] or 0), h) for h in stall), reverse=True)[:8]
-        print("\ntop warp stall reasons (pc samples, first launch):")
+    for r in rows[2:] if stall else []:
+        vals = sorted(((float(r[hdr.index(h)] or 0), h) for h in stall), reverse=True)[:6]
+        tot = sum(float(r[hdr.index(h)] or 0) for h in stall) or 1.0
+        print(f"\ntop warp stall reasons (pc samples) of {r[hdr.index('Kernel Name')][:60]}:")
         for v, h in vals:
-            print(f"  {h.replace('smsp__pcsamp_warps_issue_stalled_', ''):40s} {v:10.0f}")
-
+            print(f"  {h.replace('smsp__pcsamp_warps_issue_stalled_', ''):40s} {v:10.0f}  {100 * v / tot:5.1f} %")
 
 if __name__ == "__main__":
     main(sys.argv[1])

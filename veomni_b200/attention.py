@@ -41,7 +41,6 @@ def _prof_end(h):
 # Forward implementation for head_dim 128: "tc" = tcgen05/TMEM pipeline (attention_tc.cu), "mma" = mma.sync kernel.
 FWD_IMPL = os.environ.get("VB200_ATTN_FWD", "tc")
 BWD_IMPL = os.environ.get("VB200_ATTN_BWD", "tc")
-# EXPERIMENTAL (not yet run on hardware): eight softmax warps in the tcgen05 forward, see attn_fwd_tc_kernel<W8>
 FWD_W8 = os.environ.get("VB200_ATTN_FWD_W8", "1") == "1"  # eight softmax warps (validated on B200: 173 vs 178 us at T=4096)
 BWD_PP = os.environ.get("VB200_ATTN_BWD_PP", "0") == "1"  # softmax warpgroups on alternate tiles ("ping-pong")
 BWD_DQ_N128 = os.environ.get("VB200_ATTN_BWD_DQ_N128", "1") == "1"  # dQ kernel with 128-row K/V tiles (N = 128 MMAs); bit-identical, -25 % (B200)

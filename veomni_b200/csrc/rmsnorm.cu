@@ -234,7 +234,7 @@ rmsnorm_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat1
     }
 }
 
-// ---- fused residual-add + RMSNorm (EXPERIMENTAL until validated on hardware) -------------------
+// ---- fused residual-add + RMSNorm (default in the decoder layer, tests/test_ops_gpu.py) -------------------
 // Forward: h = bf16(x + residual) (the new residual stream, as the reference's `hidden_states = residual +
 // hidden_states` rounds it), y = bf16(w * bf16(h * rstd)) — one pass over x and residual instead of an elementwise add
 // kernel followed by the norm. One warp per row, the row's h kept packed in registers between the two sweeps;
