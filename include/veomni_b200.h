@@ -263,7 +263,8 @@ int vb200_reduce_scatter_push_bf16(void* comm, int32_t channel, int64_t region_o
  * to dst + p*dst_peer_stride + row*dst_row_stride.                                            */
 int vb200_all_to_all(void* comm, int32_t channel, int64_t region_offset, int32_t n_desc, const int64_t* desc,
                      int32_t num_ctas, void* stream);
-/* Variable-size block pull for the EP token exchange (veomni/distributed/moe/comm.py:36-42):
+/* Variable-size block pull for the EP token exchange (veomni/distributed/moe/comm.py:36-42) and the uneven image-row
+ * exchange (_AlltoAllRegion, veomni/distributed/sequence_parallel/ulysses.py:298-316):
  * chunks = device array of {int64 src_off, int64 dst_off, int64 bytes, int32 peer, int32 pad}.  */
 int vb200_chunk_pull(void* comm, int32_t channel, int64_t region_offset, const void* chunks, int32_t nchunks,
                      void* dst, int32_t num_ctas, void* stream);

@@ -43,6 +43,17 @@ def gather_heads_scatter_seq(xs, head_dim: int, seq_dim: int):
     return all_to_all_tensor(out, scatter_dim=seq_dim, gather_dim=head_dim)
 
 
+def all_to_all_rows(xs: list[torch.Tensor], splits: list[list[int]]) -> list[torch.Tensor]:
+    """``_AlltoAllRegion.forward`` (veomni/distributed/sequence_parallel/ulysses.py:298-310) on every rank of a group at
+    once: rank ``s`` splits its rows by ``splits[s]`` (``x.split(input_splits)``), ``dist.all_to_all`` hands block ``d`` to
+    rank ``d``, and the receiver concatenates what it got in source-rank order. The reference's list-form all-to-all does
+    not run on gloo, so this restatement of the definition is the checker: **parity unpinned** against an
+    executed reference for this one function (it is pure indexing)."""
+    world = len(xs)
+    blocks = [list(x[: sum(sp)].split(list(sp), dim=0)) for x, sp in zip(xs, splits)]
+    return [torch.cat([blocks[s][d] for s in range(world)], dim=0) for d in range(world)]
+
+
 def repeat_kv_for_ulysses(key: torch.Tensor, ulysses_size: int) -> torch.Tensor:
     """KV head replication when P > Hkv.  Reference: veomni/ops/kernels/attention/__init__.py:245-255.
     key: [..., S, Hkv, D] with heads at dim -2."""

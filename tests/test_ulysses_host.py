@@ -6,7 +6,7 @@ import torch
 
 from oracle import comm as o_comm
 from veomni_b200._lib import VB200Error
-from veomni_b200.ulysses import a2a_plan
+from veomni_b200.ulysses import a2a_plan, images_chunks
 
 
 def _emulate(xs, scatter_dim, gather_dim):
@@ -57,3 +57,36 @@ def test_unsupported_layouts_fail_loudly():
         a2a_plan((2, 6, 8, 16), 2, 1, 2, 2)  # batch > 1
     with pytest.raises(VB200Error):
         a2a_plan((6, 7, 16), 1, 0, 2, 2)  # heads not divisible
+
+
+@pytest.mark.parametrize("world,seed", [(2, 0), (4, 1), (8, 2)])
+def test_image_row_exchange_chunks_vs_oracle(world, seed):
+    """The block list all_to_all_images hands to vb200_chunk_pull, interpreted on host byte buffers, reproduces the
+    definition of the reference's uneven row exchange (oracle.comm.all_to_all_rows) — zero-row blocks included — and the
+    transposed split matrix gives the backward exchange."""
+    g = torch.Generator().manual_seed(seed)
+    splits = torch.randint(0, 5, (world, world), generator=g)
+    splits[0, world - 1] = 0
+    H = 24  # 48-byte rows
+    xs = [torch.randn(int(splits[s].sum()), H, generator=g).to(torch.bfloat16) for s in range(world)]
+    ref = o_comm.all_to_all_rows(xs, splits.tolist())
+    row = H * 2
+
+    def pull(bufs, mat, r):
+        ch = images_chunks(mat, r, row)
+        assert ch.dtype == torch.int64 and ch.shape == (world, 4) and ch.is_contiguous()
+        out = np.zeros(int(mat[:, r].sum()) * row, dtype=np.uint8)
+        for src_off, dst_off, nbytes, peer in ch.tolist():
+            assert src_off % 16 == 0 and dst_off % 16 == 0 and nbytes % 16 == 0
+            src = bufs[peer].contiguous().view(torch.uint8).numpy().reshape(-1)
+            out[dst_off : dst_off + nbytes] = src[src_off : src_off + nbytes]
+        if out.size == 0:
+            return torch.zeros(0, H, dtype=torch.bfloat16)
+        return torch.from_numpy(out).view(torch.bfloat16).view(-1, H)
+
+    outs = [pull(xs, splits, r) for r in range(world)]
+    for r in range(world):
+        assert torch.equal(outs[r], ref[r])
+    back = [pull(outs, splits.t().contiguous(), r) for r in range(world)]  # backward == the exchange with the roles swapped
+    for r in range(world):
+        assert torch.equal(back[r], xs[r])

@@ -168,6 +168,42 @@ def check_ulysses(symm: SymmetricMemory, dev) -> str:
     return "bit-exact"
 
 
+def check_images(symm: SymmetricMemory, dev) -> str:
+    """Uneven row exchange (``all_to_all_images``, ulysses.py:298-324): output == the blocks addressed to this rank in
+    source order; gradient == the blocks of the peers' output gradients that came from this rank. Zero-row blocks included."""
+    from . import ulysses as U
+
+    rank, world = symm.rank, symm.world
+    for trial, H in ((0, 64), (1, 1152)):
+        splits = [[(3 * s + 5 * d + trial) % 7 * (1 + 40 * trial) for d in range(world)] for s in range(world)]
+        ins, outs = splits[rank], [splits[s][rank] for s in range(world)]
+        g = torch.Generator(device="cpu").manual_seed(11 * rank + trial)
+        x = torch.randn(sum(ins) + 3, H, generator=g).to(BF).to(dev).requires_grad_(True)  # 3 trailing rows are dropped
+        y = U.all_to_all_images(x, ins, outs, group=symm.group, symm=symm)
+        cap = max(sum(r) for r in splits) + 3
+        pad = torch.zeros(cap, H, dtype=BF, device=dev)
+        pad[: x.shape[0]] = x.detach()
+        xs = _gather_all(pad, symm.group)
+        ref = torch.cat([xs[s][sum(splits[s][:rank]) : sum(splits[s][:rank]) + splits[s][rank]] for s in range(world)], dim=0)
+        if y.shape != ref.shape or not torch.equal(y.detach(), ref):
+            _fail(f"all_to_all_images forward, trial {trial}")
+        dy = torch.randn(y.shape, generator=g).to(BF).to(dev)
+        y.backward(dy)
+        capo = max(sum(splits[s][d] for s in range(world)) for d in range(world))
+        pad = torch.zeros(max(capo, 1), H, dtype=BF, device=dev)
+        pad[: dy.shape[0]] = dy
+        dys = _gather_all(pad, symm.group)
+        parts = []
+        for d in range(world):
+            o = sum(splits[s][d] for s in range(rank))
+            parts.append(dys[d][o : o + splits[rank][d]])
+        ref_dx = torch.cat(parts + [torch.zeros(3, H, dtype=BF, device=dev)], dim=0)
+        if not torch.equal(x.grad, ref_dx):
+            _fail(f"all_to_all_images backward, trial {trial}")
+    symm.check()
+    return "bit-exact"
+
+
 def check_ep_dispatch(symm: SymmetricMemory, dev) -> str:
     """Dispatched tokens == expert-major / source-minor / token-order selection of the gathered inputs; combine with
     unit weights returns K * hidden (exact in bf16 for K a power of two)."""
@@ -276,6 +312,7 @@ def run_all(symm: SymmetricMemory, dev, fsdp: bool = True, ep: bool = True) -> d
     out.update(check_reduce_scatter(symm, dev))
     out["reduce_scatter_fused_copy_in"] = check_reduce_scatter_push(symm, dev)
     out["ulysses_all_to_all"] = check_ulysses(symm, dev)
+    out["ulysses_all_to_all_images"] = check_images(symm, dev)
     if ep:
         out["ep_dispatch_combine"] = check_ep_dispatch(symm, dev)
     if fsdp:

@@ -23,6 +23,8 @@ from ._lib import VB200Error
 from .symm import SymmetricMemory, get_symmetric_memory
 
 CH_ULYSSES = 2
+CH_IMAGES_SPLITS = 6
+CH_IMAGES = 7
 
 
 def a2a_plan(shape: tuple[int, ...], scatter_dim: int, gather_dim: int, world: int, itemsize: int):
@@ -80,6 +82,19 @@ class _Stage:
         if key not in self.bufs:
             self.bufs[key] = self.symm.empty((nbytes,), torch.uint8, arena="misc")
         return self.bufs[key]
+
+    def grow(self, tag: str, nbytes: int) -> torch.Tensor:
+        """ONE buffer per tag, grown geometrically (payloads whose size changes from call to call: image rows). The old
+        block returns to the arena; every collective publishes the offset of the buffer it exposes and is stream-ordered
+        after the previous user, so ranks growing at different times is fine."""
+        nbytes = (max(int(nbytes), 1) + 255) // 256 * 256
+        cur = self.bufs.get((tag, 0))
+        if cur is None or cur.numel() < nbytes:
+            want = nbytes if cur is None else max(nbytes, cur.numel() * 3 // 2)
+            self.bufs.pop((tag, 0), None)
+            del cur
+            self.bufs[(tag, 0)] = self.symm.empty(((want + 255) // 256 * 256,), torch.uint8, arena="misc")
+        return self.bufs[(tag, 0)]
 
 
 _stages: dict[int, _Stage] = {}
@@ -210,10 +225,95 @@ def gather_heads_scatter_seq(x: torch.Tensor, head_dim: int, seq_dim: int, group
     return _SeqAllToAll.apply(group, x, seq_dim, head_dim)
 
 
+def images_chunks(splits: torch.Tensor, rank: int, row_bytes: int) -> torch.Tensor:
+    """Block list of one uneven row exchange. ``splits[s, d]`` (integer tensor, host or device) = rows rank ``s`` sends to
+    rank ``d``; returns int64 ``[world, 4]`` = {src_off, dst_off, bytes, peer} as the C struct ``ChunkDesc`` (csrc/p2p.cu)
+    for ``rank``'s pull: the block from source ``s`` sits in ``s``'s send buffer behind the rows ``s`` sends to lower
+    ranks, and lands behind the blocks of lower sources (``torch.cat(output_tensor_list)`` order, ulysses.py:309)."""
+    splits = splits.to(torch.int64)
+    world = splits.shape[0]
+    excl = torch.cumsum(splits, dim=1) - splits
+    n = splits[:, rank]
+    dst = torch.cumsum(n, dim=0) - n
+    peer = torch.arange(world, dtype=torch.int64, device=splits.device)
+    return torch.stack([excl[:, rank] * row_bytes, dst * row_bytes, n * row_bytes, peer], dim=1).contiguous()
+
+
+def _pull_rows(symm: SymmetricMemory, x: torch.Tensor, splits_dev: torch.Tensor, n_out: int, num_ctas: int) -> torch.Tensor:
+    """Stage ``x`` (this rank's rows, grouped by destination) and pull the blocks addressed to this rank."""
+    from . import _lib
+    from ._lib import check, stream_ptr
+
+    row_bytes = x[0].numel() * x.element_size() if x.shape[0] else _numel(x.shape[1:]) * x.element_size()
+    if row_bytes % 16:
+        raise VB200Error(f"all_to_all_images: rows of {row_bytes} bytes are not a multiple of 16")
+    stage = _stage_for(symm)
+    buf = stage.grow("images", x.numel() * x.element_size())
+    if x.numel():
+        buf[: x.numel() * x.element_size()].view(x.dtype).view(x.shape).copy_(x)
+    out = torch.empty((max(n_out, 1), *x.shape[1:]), dtype=x.dtype, device=x.device)[:n_out]
+    chunks = images_chunks(splits_dev, symm.rank, row_bytes)
+    with torch.cuda.device(x.device), prof.span("images_a2a", out.numel() * out.element_size()):
+        check(_lib.load().vb200_chunk_pull(symm.comm, CH_IMAGES, symm.offset_of(buf), chunks.data_ptr(), symm.world,
+                                           out.data_ptr(), num_ctas, stream_ptr()), "vb200_chunk_pull")
+    return out
+
+
+class _AlltoAllRegion(torch.autograd.Function):
+    """Same contract as the reference's ``_AlltoAllRegion`` (ulysses.py:298-316): uneven row exchange along dim 0,
+    backward = the exchange with the split lists swapped. The reference issues a list-form ``dist.all_to_all``; here the
+    ``[world, world]`` split matrix is all-gathered through the symmetric region (``world`` ints per rank, no host
+    read-back), the block list is computed from it on the device, and ONE pull kernel moves the rows."""
+
+    @staticmethod
+    def forward(ctx: Any, group, x: torch.Tensor, input_splits, output_splits, num_ctas: int = 16, symm=None):
+        symm = symm if symm is not None else get_symmetric_memory(group)
+        if not x.is_cuda:
+            raise VB200Error("all_to_all_images runs on CUDA tensors only (no gloo/CPU fallback)")
+        if len(input_splits) != symm.world or len(output_splits) != symm.world or sum(input_splits) != x.shape[0]:
+            raise VB200Error("all_to_all_images: split lists must have one entry per rank and cover the rows of x")
+        w = symm.world
+        mat = _stage_for(symm).grow("images_splits", w * w * 4).view(torch.int32)[: w * w]
+        mat[symm.rank * w : (symm.rank + 1) * w].copy_(torch.tensor(list(input_splits), dtype=torch.int32), non_blocking=True)
+        symm.all_gather_inplace(mat, w, CH_IMAGES_SPLITS, 1)
+        splits = mat.view(w, w).to(torch.int64)  # a copy: the staging matrix is reused by the next call
+        ctx.symm, ctx.num_ctas, ctx.n_in = symm, num_ctas, int(x.shape[0])
+        ctx.save_for_backward(splits)
+        return _pull_rows(symm, x.contiguous(), splits, int(sum(output_splits)), num_ctas)
+
+    @staticmethod
+    def backward(ctx: Any, dy: torch.Tensor):
+        (splits,) = ctx.saved_tensors
+        dx = _pull_rows(ctx.symm, dy.contiguous(), splits.t().contiguous(), ctx.n_in, ctx.num_ctas)
+        return None, dx, None, None, None, None
+
+
+def all_to_all_images(image_embeds: torch.Tensor, in_splits, out_splits, group: dist.ProcessGroup | None = None,
+                      symm: SymmetricMemory | None = None):
+    """Drop-in for veomni.distributed.sequence_parallel.ulysses.all_to_all_images (:319-324): balance the vision tower's
+    image embeddings over the Ulysses group (``in_splits[d]`` rows go to rank ``d``, ``out_splits[s]`` rows arrive from
+    rank ``s``); an empty ``in_splits`` is the identity, rows beyond ``sum(in_splits)`` are dropped."""
+    if not in_splits:
+        return image_embeds
+    image_embeds = image_embeds[: sum(in_splits)]
+    if group is None:
+        from .parallel_state import get_parallel_state
+
+        ps = get_parallel_state()
+        if not ps.ulysses_enabled:
+            return image_embeds
+        group = ps.ulysses_group
+    if dist.get_world_size(group) == 1:
+        return image_embeds
+    return _AlltoAllRegion.apply(group, image_embeds, list(in_splits), list(out_splits), 16, symm)
+
+
 def install() -> None:
-    """Route VeOmni's Ulysses exchange through this module (no-op if VeOmni is not importable)."""
+    """Route VeOmni's Ulysses exchanges through this module (no-op if VeOmni is not importable)."""
     try:
+        from veomni.distributed import sequence_parallel as pkg
         from veomni.distributed.sequence_parallel import ulysses as ref
     except ImportError:
         return
     ref.all_to_all_tensor = all_to_all_tensor
+    ref.all_to_all_images = pkg.all_to_all_images = all_to_all_images
