@@ -233,3 +233,69 @@ def test_ep_plan_chunks_matches_the_loop_restatement():
                     exp_bwd.append([(base + int(counts[:r, e].sum())) * row, int(excl[r, e]) * row, int(counts[r, e]) * row, p])
                     base += int(tot[e])
             assert bwd.tolist() == exp_bwd
+
+
+def _wrap_worker(rank, world, ep, path, outdir):
+    """Our build_parallelize_model on the host toy Qwen3-MoE, 2 or 4 gloo ranks, NCCL-free (b200_comm off: CPU)."""
+    import json
+    import sys
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", store=dist.FileStore(path, world), rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_wrap_structure import TOY, describe
+    from veomni_b200.host_qwen3_moe import Qwen3MoeConfig, Qwen3MoeForCausalLM
+    from veomni_b200.parallel_state import init_parallel_state
+    from veomni_b200.parallelize import build_parallelize_model
+
+    init_parallel_state(dp_size=world, dp_shard_size=world, ulysses_size=1, ep_size=ep, device_type="cpu")
+    cfg = Qwen3MoeConfig(**{k: TOY[k] for k in (
+        "vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "num_key_value_heads",
+        "head_dim", "rms_norm_eps", "rope_theta", "tie_word_embeddings", "initializer_range", "num_experts",
+        "num_experts_per_tok", "moe_intermediate_size", "norm_topk_prob")})
+    with torch.device("meta"):
+        model = Qwen3MoeForCausalLM(cfg)
+    model = build_parallelize_model(model, init_device="meta", b200_comm=False, enable_reshard_after_forward=True,
+                                    enable_gradient_checkpointing=True, enable_forward_prefetch=True)
+    res = describe(model)
+    res["finite"] = all(bool(torch.isfinite(p.to_local()).all()) for p in model.parameters())
+    with open(os.path.join(outdir, f"r{rank}.json"), "w") as fh:
+        json.dump(res, fh)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ep", [(2, 2), (4, 2), (2, 1)])
+def test_wrap_structure_matches_the_reference_gloo(world, ep):
+    """``build_parallelize_model`` (EP slice + experts Shard(1) on ep_fsdp + bottom-up FSDP2 + prefetch lists + meta init)
+    produces the same FSDP2 structure as the reference's own function on the same toy Qwen3-MoE
+    (tests/golden/wrap_structure.json, generated by running the unmodified reference on gloo: make_wrap_structure.py):
+    same units on the same meshes with the same placements / local shapes / dtypes / divide factors / prefetch targets."""
+    import json
+
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wrap_structure.json")))
+    run = next(r for r in ref["runs"] if r["world"] == world and r["ep_size"] == ep)
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_wrap_worker, args=(world, ep, os.path.join(d, "store"), d), nprocs=world, join=True)
+        for r in range(world):
+            mine, want = json.load(open(os.path.join(d, f"r{r}.json"))), run["ranks"][r]
+            assert mine["finite"] and mine["all_dtensor"] and mine["has_clip"] and mine["grad_ckpt"]
+            assert mine["param_dtypes"] == want["param_dtypes"] == ["torch.float32"]
+            assert mine["ep_sliced_fqns"] == want["ep_sliced_fqns"]
+            assert [u["module"] for u in mine["units"]] == [u["module"] for u in want["units"]]
+            for a, b in zip(mine["units"], want["units"]):
+                for k in ("cls", "reshard_after_forward", "auto_reshard_after_forward", "gradient_divide_factor", "param_dtype",
+                          "reduce_dtype", "backward_prefetch"):
+                    assert a[k] == b[k], (a["module"], k, a[k], b[k])
+                assert [s for _n, s in a["mesh"]] == [s for _n, s in b["mesh"]], (a["module"], a["mesh"], b["mesh"])
+                assert sorted(map(json.dumps, a["params"])) == sorted(map(json.dumps, b["params"])), a["module"]
+                if ep > 1:
+                    assert a["forward_prefetch"] == b["forward_prefetch"], (a["module"], a["forward_prefetch"])
+            if ep == 1:
+                # the reference sets no explicit lists without EP (FSDP2's implicit prefetch); ours chains root -> layer 0 ->
+                # layer 1 ... so that the overlap does not depend on host timing (parallelize.py, "explicit forward prefetch")
+                chain = {u["module"]: u["forward_prefetch"] for u in mine["units"]}
+                L = ref["toy_config"]["num_hidden_layers"]
+                assert chain[""] == ["model.layers.0"] and chain[f"model.layers.{L - 1}"] == []
+                assert all(chain[f"model.layers.{i}"] == [f"model.layers.{i + 1}"] for i in range(L - 1))

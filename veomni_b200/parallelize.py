@@ -78,7 +78,7 @@ def build_parallelize_model(
         if ps.device_mesh is not None:
             mesh = ps.fsdp_mesh  # 2-D (dp_replicate, dp_shard[_sp]) under HSDP
         else:
-            mesh = init_device_mesh("cuda", (world,), mesh_dim_names=("dp_shard",))
+            mesh = init_device_mesh("cuda" if torch.cuda.is_available() else "cpu", (world,), mesh_dim_names=("dp_shard",))
     shard_group = mesh.get_group(mesh.ndim - 1)  # the reduce-scatter / all-gather group (last mesh dim)
     mp = MixedPrecisionPolicy(param_dtype=param_dtype, reduce_dtype=reduce_dtype)
     fsdp_kwargs = dict(mesh=mesh, mp_policy=mp, reshard_after_forward=enable_reshard_after_forward)
@@ -140,7 +140,8 @@ def build_parallelize_model(
 
     # ---- meta init --------------------------------------------------------------------------------------------------
     if init_device == "meta":
-        model.to_empty(device=torch.device("cuda", torch.cuda.current_device()))
+        on_gpu = mesh.device_type == "cuda"  # CPU meshes (gloo) only in the host-logic tests
+        model.to_empty(device=torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu"))
         model.init_weights()
 
     # ---- the NVLink collectives ---------------------------------------------------------------------------------------
