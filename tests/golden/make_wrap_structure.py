@@ -25,7 +25,8 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 REF = "/root/reference"
-WORLDS = [(2, 2), (4, 2), (2, 1)]  # (world, ep_size): ep_fsdp = 1, ep_fsdp = 2, dense-only
+# (world, ep_size, dp_replicate): ep_fsdp = 1, ep_fsdp = 2, dense-only, HSDP (2 replicas x 2 shards)
+WORLDS = [(2, 2, 1), (4, 2, 1), (2, 1, 1), (4, 1, 2)]
 TOY = dict(architectures=["Qwen3MoeForCausalLM"], model_type="qwen3_moe", hidden_size=64, intermediate_size=128,
            moe_intermediate_size=32, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2, head_dim=16,
            num_experts=8, num_experts_per_tok=2, norm_topk_prob=True, decoder_sparse_step=1, mlp_only_layers=[],
@@ -75,7 +76,7 @@ def describe(model) -> dict:
                                                                                or getattr(model, "gradient_checkpointing", False))}
 
 
-def _worker(rank: int, world: int, ep: int, store: str, cfg_dir: str, out: str):
+def _worker(rank: int, world: int, ep: int, rep: int, store: str, cfg_dir: str, out: str):
     os.environ.update(MASTER_ADDR="127.0.0.1", RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       OMP_NUM_THREADS="1")
     sys.path.insert(0, REF)
@@ -98,8 +99,8 @@ def _worker(rank: int, world: int, ep: int, store: str, cfg_dir: str, out: str):
     from veomni.distributed.torch_parallelize import build_parallelize_model
     from veomni.models import build_foundation_model
 
-    init_parallel_state(dp_size=world, dp_shard_size=world, ulysses_size=1, dp_mode="fsdp2", device_type="cpu",
-                        extra_parallel_sizes=(ep,))
+    init_parallel_state(dp_size=world, dp_replicate_size=rep, dp_shard_size=world // rep, ulysses_size=1, dp_mode="fsdp2",
+                        device_type="cpu", extra_parallel_sizes=(ep,))
     model = build_foundation_model(config_path=cfg_dir, torch_dtype="float32", attn_implementation="sdpa", init_device="meta",
                                    ops_implementation=make_eager_ops_config())
     cpu_load = getattr(model.get_parallel_plan(), "cpu_load_param_name", None) if hasattr(model, "get_parallel_plan") else None
@@ -123,13 +124,13 @@ def main():
         cfg = Path(d) / "cfg"
         cfg.mkdir()
         (cfg / "config.json").write_text(json.dumps(TOY))
-        for world, ep in WORLDS:
-            out = Path(d) / f"w{world}e{ep}"
+        for world, ep, rep in WORLDS:
+            out = Path(d) / f"w{world}e{ep}r{rep}"
             out.mkdir()
-            mp.spawn(_worker, args=(world, ep, str(out / "store"), str(cfg), str(out)), nprocs=world, join=True)
+            mp.spawn(_worker, args=(world, ep, rep, str(out / "store"), str(cfg), str(out)), nprocs=world, join=True)
             ranks = [json.loads((out / f"r{r}.json").read_text()) for r in range(world)]
-            result["runs"].append({"world": world, "ep_size": ep, "ranks": ranks})
-            print(f"world {world} ep {ep}: {len(ranks[0]['units'])} FSDP units, ep-sliced {len(ranks[0]['ep_sliced_fqns'])}")
+            result["runs"].append({"world": world, "ep_size": ep, "dp_replicate": rep, "ranks": ranks})
+            print(f"world {world} ep {ep} replicas {rep}: {len(ranks[0]['units'])} FSDP units, ep-sliced {len(ranks[0]['ep_sliced_fqns'])}")
     (HERE / "wrap_structure.json").write_text(json.dumps(result, indent=1))
     print("wrote", HERE / "wrap_structure.json")
 

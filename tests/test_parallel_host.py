@@ -235,7 +235,7 @@ def test_ep_plan_chunks_matches_the_loop_restatement():
             assert bwd.tolist() == exp_bwd
 
 
-def _wrap_worker(rank, world, ep, path, outdir):
+def _wrap_worker(rank, world, ep, rep, path, outdir):
     """Our build_parallelize_model on the host toy Qwen3-MoE, 2 or 4 gloo ranks, NCCL-free (b200_comm off: CPU)."""
     import json
     import sys
@@ -249,7 +249,8 @@ def _wrap_worker(rank, world, ep, path, outdir):
     from veomni_b200.parallel_state import init_parallel_state
     from veomni_b200.parallelize import build_parallelize_model
 
-    init_parallel_state(dp_size=world, dp_shard_size=world, ulysses_size=1, ep_size=ep, device_type="cpu")
+    init_parallel_state(dp_size=world, dp_replicate_size=rep, dp_shard_size=world // rep, ulysses_size=1, ep_size=ep,
+                        device_type="cpu")
     cfg = Qwen3MoeConfig(**{k: TOY[k] for k in (
         "vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "num_key_value_heads",
         "head_dim", "rms_norm_eps", "rope_theta", "tie_word_embeddings", "initializer_range", "num_experts",
@@ -266,18 +267,19 @@ def _wrap_worker(rank, world, ep, path, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,ep", [(2, 2), (4, 2), (2, 1)])
-def test_wrap_structure_matches_the_reference_gloo(world, ep):
+@pytest.mark.parametrize("world,ep,rep", [(2, 2, 1), (4, 2, 1), (2, 1, 1), (4, 1, 2)])
+def test_wrap_structure_matches_the_reference_gloo(world, ep, rep):
     """``build_parallelize_model`` (EP slice + experts Shard(1) on ep_fsdp + bottom-up FSDP2 + prefetch lists + meta init)
-    produces the same FSDP2 structure as the reference's own function on the same toy Qwen3-MoE
+    produces the same FSDP2 structure — EP with ep_fsdp 1 and 2, dense, and HSDP (2 replicas x 2 shards) — as the reference's
+    own function on the same toy Qwen3-MoE
     (tests/golden/wrap_structure.json, generated by running the unmodified reference on gloo: make_wrap_structure.py):
     same units on the same meshes with the same placements / local shapes / dtypes / divide factors / prefetch targets."""
     import json
 
     ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "wrap_structure.json")))
-    run = next(r for r in ref["runs"] if r["world"] == world and r["ep_size"] == ep)
+    run = next(r for r in ref["runs"] if (r["world"], r["ep_size"], r["dp_replicate"]) == (world, ep, rep))
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_wrap_worker, args=(world, ep, os.path.join(d, "store"), d), nprocs=world, join=True)
+        mp.spawn(_wrap_worker, args=(world, ep, rep, os.path.join(d, "store"), d), nprocs=world, join=True)
         for r in range(world):
             mine, want = json.load(open(os.path.join(d, f"r{r}.json"))), run["ranks"][r]
             assert mine["finite"] and mine["all_dtensor"] and mine["has_clip"] and mine["grad_ckpt"]
