@@ -117,7 +117,38 @@ def bench_attention(dev, iters):
         print({"flash_attn": str(ex)})
 
 
-BENCHES = {"attention": bench_attention}
+def bench_moe_ep8(dev, iters):
+    """GroupGEMM at the per-rank shape of BASELINE configs[3] (Qwen3-30B-A3B, EP8): 16 local experts, the T*K = 32768 rows a
+    rank receives on average (multinomial split, ~2048 rows per expert), H=2048, I=768. Unlike the 128-local-expert shape
+    of ``bench_moe`` (805 MB of weights per 206 GFLOP: below the HBM ridge) this one is tensor-bound."""
+    from veomni_b200.moe import group_gemm_same_mn, group_gemm_same_nk
+
+    E, R, H, I = 16, 32768, 2048, 768
+    g = torch.Generator(device=dev).manual_seed(1)
+    counts = torch.bincount(torch.randint(0, E, (R,), device=dev, generator=g), minlength=E)
+    cumsum = torch.cumsum(counts, 0).to(torch.int32)
+    x = (0.1 * torch.randn(R, H, device=dev, generator=g)).to(BF)
+    w1 = (0.1 * torch.randn(E, 2 * I, H, device=dev, generator=g)).to(BF)
+    w2 = (0.1 * torch.randn(E, H, I, device=dev, generator=g)).to(BF)
+    with torch.no_grad():
+        report("ep8 group_gemm_NT fc1[32768x2048 -> 1536, 16e]", time_fn(lambda: group_gemm_same_nk(x, w1, cumsum, transpose_b=True), [()], iters),
+               flops=2 * R * 2 * I * H)
+        a = group_gemm_same_nk(x, w1, cumsum, transpose_b=True)
+        act = a[:, :I].contiguous()
+        report("ep8 group_gemm_NT fc2[32768x768 -> 2048, 16e]", time_fn(lambda: group_gemm_same_nk(act, w2, cumsum, transpose_b=True), [()], iters),
+               flops=2 * R * I * H)
+        report("ep8 group_gemm_NN dgrad fc1[32768x1536 -> 2048, 16e]", time_fn(lambda: group_gemm_same_nk(a, w1, cumsum, transpose_b=False), [()], iters),
+               flops=2 * R * 2 * I * H)
+        gw = torch.empty_like(w1)
+        report("ep8 group_gemm_TN wgrad fc1[16 x 1536x2048, K=32768]", time_fn(lambda: group_gemm_same_mn(a, x, gw, cumsum), [()], iters),
+               flops=2 * R * 2 * I * H)
+        gw2 = torch.empty_like(w2)
+        go = (0.1 * torch.randn(R, H, device=dev, generator=g)).to(BF)
+        report("ep8 group_gemm_TN wgrad fc2[16 x 2048x768, K=32768]", time_fn(lambda: group_gemm_same_mn(go, act, gw2, cumsum), [()], iters),
+               flops=2 * R * I * H)
+
+
+BENCHES = {"attention": bench_attention, "moe_ep8": bench_moe_ep8}
 
 
 def bench_moe(dev, iters):
@@ -149,6 +180,10 @@ def bench_moe(dev, iters):
         gw = torch.empty_like(w1)
         report("group_gemm_TN wgrad fc1[128 x 1536x2048, K=32768]", time_fn(lambda: group_gemm_same_mn(a, x, gw, cumsum), [()], iters),
                flops=2 * T * K * 2 * I * H)
+        gw2 = torch.empty_like(w2)
+        go = (0.1 * torch.randn(T * K, H, device=dev, generator=g)).to(BF)
+        report("group_gemm_TN wgrad fc2[128 x 2048x768, K=32768]", time_fn(lambda: group_gemm_same_mn(go, act, gw2, cumsum), [()], iters),
+               flops=2 * T * K * I * H)
     hs_g, w1_g, w2_g, rw_g = (t.clone().requires_grad_(True) for t in (hs, w1, w2, rw))
 
     def fb():

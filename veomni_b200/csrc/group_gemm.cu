@@ -40,7 +40,10 @@ struct GGParams {
     int G;
     int M, N, K;  // NT/NN: N, K = per-group GEMM dims (M unused); TN: M, N = output dims (K unused)
     __nv_bfloat16* C;
+    int staged_epi;  // group_gemm_kernel: epilogue rows leave through a per-warp smem transpose (coalesced 64-byte row segments)
 };
+constexpr int GG_EPI_ROW = 80;                       // bytes per staged row: 64 of payload + 16 of padding (bank spread)
+constexpr int GG_EPI_STAGE = 32 * GG_EPI_ROW;        // one warp's 32 rows x 32 bf16 columns
 
 // Tile bookkeeping shared by the three roles.
 struct TileInfo {
@@ -93,6 +96,7 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     int* tile_start = reinterpret_cast<int*>(tmem_slot + 2);  // [G+1]
+    uint8_t* epi_stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tile_start + p.G + 1) + 15) & ~uintptr_t(15));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int n_tiles_n = (p.N + GG_BN - 1) / GG_BN;
@@ -236,7 +240,38 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0u;
                 }
-                if (row_ok) {
+                if (p.staged_epi && c * 32 + 32 <= ncols) {
+                    // A thread owns a ROW of the accumulator (TMEM lane): storing its 64 bytes directly makes every store
+                    // instruction of the warp touch 32 different 128-byte lines, 16 bytes each — 4096 such line requests
+                    // per 128x256 tile, which is what bounded the wgrad (K_g ~ 256: 2048 clk of MMA per tile, ~7900 clk
+                    // measured per tile, tensor pipe 30 %; profiles/r02_topkernels_ncu.txt). Transposed through a
+                    // padded per-warp staging block, an instruction writes 8 rows x 64 contiguous bytes instead.
+                    uint8_t* stg = epi_stage + (warp - 2) * GG_EPI_STAGE;
+                    __syncwarp();  // the previous chunk's read-back is complete
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 o;
+                        o.x = f2_to_bf2(__uint_as_float(v[i * 8 + 0]), __uint_as_float(v[i * 8 + 1]));
+                        o.y = f2_to_bf2(__uint_as_float(v[i * 8 + 2]), __uint_as_float(v[i * 8 + 3]));
+                        o.z = f2_to_bf2(__uint_as_float(v[i * 8 + 4]), __uint_as_float(v[i * 8 + 5]));
+                        o.w = f2_to_bf2(__uint_as_float(v[i * 8 + 6]), __uint_as_float(v[i * 8 + 7]));
+                        *reinterpret_cast<uint4*>(stg + lane * GG_EPI_ROW + i * 16) = o;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int rr = j * 8 + (lane >> 2), ch = lane & 3;  // row inside the warp's 32, 16-byte piece of its 64
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * GG_EPI_ROW + ch * 16);
+                        const int r2 = q * 32 + rr;
+                        if (MODE == GG_TN) {
+                            const int m2 = ti.mt * GG_BM + r2;
+                            if (m2 < p.M)
+                                __stcs(reinterpret_cast<uint4*>(p.C + ((int64_t)ti.g * p.M + m2) * p.N + ti.nt * GG_BN + c * 32 + ch * 8), val);
+                        } else if (r2 < ti.rows_valid) {
+                            *reinterpret_cast<uint4*>(p.C + (int64_t)(ti.row0 + r2) * p.N + ti.nt * GG_BN + c * 32 + ch * 8) = val;
+                        }
+                    }
+                } else if (row_ok) {
                     if (c * 32 + 32 <= ncols) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -678,8 +713,9 @@ group_gemm_swap2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     }
 }
 
-static size_t gg_smem_bytes(int G) {
-    return (size_t)GG_STAGES * GG_STAGE_BYTES + (2 * GG_STAGES + 4) * 8 + 16 + (size_t)(G + 1) * 4 + 64;
+static size_t gg_smem_bytes(int G) {  // stages | barriers | tmem slot | tile_start[G+1] | epilogue staging (16-byte aligned)
+    return (size_t)GG_STAGES * GG_STAGE_BYTES + (2 * GG_STAGES + 4) * 8 + 16 + (size_t)(G + 1) * 4 + 64 +
+           (size_t)GG_EPI_WARPS * GG_EPI_STAGE;
 }
 
 }  // namespace vb
@@ -704,6 +740,12 @@ extern "C" int vb200_group_gemm(int32_t mode, const void* a, const void* b, void
     p.cumsum = cumsum; p.G = num_groups; p.M = m; p.N = n; p.K = k; p.C = (__nv_bfloat16*)c;
     const uint64_t rows = (uint64_t)(total_rows > 0 ? total_rows : 1);
     const size_t smem = gg_smem_bytes(num_groups);
+    static int staged = -1;
+    if (staged < 0) {
+        const char* e = getenv("VB200_GG_EPI_STAGED");
+        staged = (e && e[0] == '0') ? 0 : 1;  // 0: every thread stores its own accumulator row (A/B runs)
+    }
+    p.staged_epi = staged;
     static int swap_mode = -1;
     if (swap_mode < 0) {
         const char* e = getenv("VB200_GG_SWAP");
