@@ -511,6 +511,7 @@ def main():
     stage("reduce-scatter with fused copy-in (generic instantiation)", selfcheck.check_reduce_scatter_push, symm, dev)
     os.environ.pop("VB200_RS_GENERIC")
     stage("ulysses", test_ulysses, rank, world, dev)
+    stage("all_to_all_images: uneven row exchange, forward + backward (self-check)", selfcheck.check_images, symm, dev)
     stage("async ulysses projections == synchronous path", test_async_ulysses, rank, world, dev)
     stage("fsdp2 custom comm", test_fsdp, rank, world, dev)
     stage("fsdp2 custom comm: every mode, ragged shapes, divide factor (self-check)", selfcheck.check_fsdp, dev, world)
