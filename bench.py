@@ -41,7 +41,8 @@ METRIC = "tokens/sec (Qwen3-8B FSDP2 bf16 seq4096)"
 CPU_SAMPLE_TOKENS = 256  # the bounded CPU sample: one definition for `cpu_baseline` and `--impl reference`
 
 # DRAM bytes per launch (read + write) of the three attention kernels at T=4096, 32/8 heads, D=128, from ncu --set full
-NCU_TRAFFIC_BYTES = {"bwd_dkdv": 86041088 + 4705024, "bwd_dq": 84966656 + 11869440, "fwd": 50374400 + 3454208}
+# (profiles/r02_topkernels_ncu.txt: attn_bwd_dkdv_tc_kernel, attn_bwd_dq_n128_kernel, attn_fwd_tc_kernel<W8>)
+NCU_TRAFFIC_BYTES = {"bwd_dkdv": 85890304 + 3582464, "bwd_dq": 84962560 + 9859072, "fwd": 50362368 + 2289920}
 
 
 def _peaks():
@@ -446,9 +447,9 @@ def run_b200(args) -> None:
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16_tflops_sustained"], 4) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-                         # the same kernel at the same shape (profiles/r0*_attn_*_ncu.txt)
+                         # the same kernel at the same shape (profiles/r02_topkernels_ncu.txt)
                          "traffic": NCU_TRAFFIC_BYTES.get(dom) if (wl == "qwen3_8b") else None,
-                         "traffic_source": "profiles/r01_attn_*_ncu.txt (ncu --set full)",
+                         "traffic_source": "profiles/r02_topkernels_ncu.txt (ncu --set full, one launch at the same shape)",
                          "peak_source": f"{peaks['how']} (sustained cuBLAS bf16, kernel timed inside a long step)",
                          "avg_launch_ms": round(attn_avg_ms, 4), "launches_timed": len(attn_ms),
                          "algorithmic_flops_per_launch": attn_flops},

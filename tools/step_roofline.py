@@ -37,7 +37,7 @@ WORK = [
     (r"vb::attn_bwd_dkdv_tc_kernel", "tensor", FWD_ATTN * 2.5 * 0.6),
     (r"vb::attn_bwd_delta_kernel", "hbm", 2 * T * HQ * D * 2),
     (r"vb::cross_entropy_kernel", "hbm", 2 * 1024 * V * 2),
-    (r"vb::multi_adamw_kernel<__nv_bfloat16, (true|1)>", "hbm", 30 * P8),           # fp32 master + 2 moments r/w, bf16 grad, bf16 copy
+    (r"vb::multi_adamw_kernel<__nv_bfloat16, (true|1)>", "hbm", 28 * P8),           # fp32 master + 2 moments read+write (24), bf16 grad read (2), bf16 copy write (2)
     (r"vb::multi_sumsq_kernel", "hbm", 2 * P8),                                       # bf16 gradients read once
 ]
 
