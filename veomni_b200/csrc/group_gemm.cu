@@ -42,7 +42,7 @@ struct GGParams {
     __nv_bfloat16* C;
     int staged_epi;  // group_gemm_kernel: epilogue rows leave through a per-warp smem transpose (coalesced 64-byte row segments)
 };
-constexpr int GG_EPI_ROW = 80;                       // bytes per staged row: 64 of payload + 16 of padding (bank spread)
+constexpr int GG_EPI_ROW = 64;                       // bytes per staged row (32 bf16); its four 16-byte pieces are XOR-swizzled
 constexpr int GG_EPI_STAGE = 32 * GG_EPI_ROW;        // one warp's 32 rows x 32 bf16 columns
 
 // Tile bookkeeping shared by the three roles.
@@ -245,7 +245,7 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     // instruction of the warp touch 32 different 128-byte lines, 16 bytes each — 4096 such line requests
                     // per 128x256 tile, which is what bounded the wgrad (K_g ~ 256: 2048 clk of MMA per tile, ~7900 clk
                     // measured per tile, tensor pipe 30 %; profiles/r02_topkernels_ncu.txt). Transposed through a
-                    // padded per-warp staging block, an instruction writes 8 rows x 64 contiguous bytes instead.
+                    // swizzled per-warp staging block, an instruction writes 8 rows x 64 contiguous bytes instead.
                     uint8_t* stg = epi_stage + (warp - 2) * GG_EPI_STAGE;
                     __syncwarp();  // the previous chunk's read-back is complete
 #pragma unroll
@@ -255,13 +255,15 @@ group_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         o.y = f2_to_bf2(__uint_as_float(v[i * 8 + 2]), __uint_as_float(v[i * 8 + 3]));
                         o.z = f2_to_bf2(__uint_as_float(v[i * 8 + 4]), __uint_as_float(v[i * 8 + 5]));
                         o.w = f2_to_bf2(__uint_as_float(v[i * 8 + 6]), __uint_as_float(v[i * 8 + 7]));
-                        *reinterpret_cast<uint4*>(stg + lane * GG_EPI_ROW + i * 16) = o;
+                        // piece i of row `lane` sits at slot i ^ ((lane >> 1) & 3): the 8 lanes of a quarter-warp then cover
+                        // all 32 banks both here (8 rows, same piece) and in the read-back (2 rows, 4 pieces)
+                        *reinterpret_cast<uint4*>(stg + lane * GG_EPI_ROW + ((i ^ ((lane >> 1) & 3)) << 4)) = o;
                     }
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int rr = j * 8 + (lane >> 2), ch = lane & 3;  // row inside the warp's 32, 16-byte piece of its 64
-                        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * GG_EPI_ROW + ch * 16);
+                        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * GG_EPI_ROW + ((ch ^ ((rr >> 1) & 3)) << 4));
                         const int r2 = q * 32 + rr;
                         if (MODE == GG_TN) {
                             const int m2 = ti.mt * GG_BM + r2;
