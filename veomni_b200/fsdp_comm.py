@@ -352,6 +352,11 @@ def _patch_copy_in() -> None:
     global _orig_copy_in, _orig_div
     from torch.distributed.fsdp._fully_shard import _fsdp_collectives as fc
 
+    # private names of torch's FSDP2 (present in 2.9 .. 2.11): fail with a clear message instead of half-patching
+    missing = [n for n in ("foreach_reduce_scatter_copy_in", "_div_if_needed", "_get_param_all_gather_inputs") if not hasattr(fc, n)]
+    if missing:
+        raise VB200Error(f"torch {torch.__version__}: FSDP2 internals {missing} not found in _fsdp_collectives; the fused "
+                         "copy-in / copy-out patches cannot be installed (use install_fsdp_comm(..., rs_mode='f32', fuse_copy_out=False))")
     if _orig_copy_in is None:
         _orig_copy_in, _orig_div = fc.foreach_reduce_scatter_copy_in, fc._div_if_needed
         fc.foreach_reduce_scatter_copy_in = _copy_in
