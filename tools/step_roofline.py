@@ -71,6 +71,7 @@ def main(path):
     print(f"{'kernel':<44} {'launches':>8} {'measured ms':>12} {'algorithmic ms':>15} {'fraction':>9}")
     s_min = s_meas = 0.0
     seen = set()
+    o_min = o_meas = 0.0  # optimizer-side kernels (AdamW, gradient norm), reported apart as well
     for pat, bound, work in WORK:
         names = [n for n in cnt if re.match(pat, n)]
         n_l = sum(cnt[n] for n in names)
@@ -81,12 +82,18 @@ def main(path):
         tmin = n_l * work / (hbm if bound == "hbm" else tensor)
         s_min += tmin
         s_meas += t_meas
+        if "multi_" in pat:
+            o_min += tmin
+            o_meas += t_meas
         label = re.sub(r"\\d\+|\(|\)|\\", "", pat)[4:]
         print(f"{label[:44]:<44} {n_l:>8d} {t_meas*1e3:>12.3f} {tmin*1e3:>15.3f} {tmin/t_meas:>9.3f}")
     other = {n: tot[n] for n in cnt if n.startswith("vb::") and n not in seen}
     for n, t in sorted(other.items(), key=lambda kv: -kv[1])[:8]:
         print(f"# not in the table: {n[:70]} {cnt[n]} launches, {t*1e3:.3f} ms")
     print(f"{'TOTAL (in-scope kernels)':<44} {'':>8} {s_meas*1e3:>12.3f} {s_min*1e3:>15.3f} {s_min/s_meas:>9.3f}")
+    if o_meas and s_meas > o_meas:
+        print(f"{'TOTAL without the optimizer kernels':<44} {'':>8} {(s_meas-o_meas)*1e3:>12.3f} {(s_min-o_min)*1e3:>15.3f} "
+              f"{(s_min-o_min)/(s_meas-o_meas):>9.3f}")
 
 
 if __name__ == "__main__":
